@@ -1,0 +1,605 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A thin extern "C" wrapper that lets the Python test/bench harness call the
+// UNMODIFIED reference (openfhe-development v1.5.1, compiled from
+// /root/reference by oracle/Makefile.ref into oracle/_ref/) on raw uint64
+// arrays.  Nothing here re-implements arithmetic: every function forwards to the
+// reference's own classes.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load the resulting libofhe_ref.so.
+//
+// Layout convention shared with the product: a DCRTPoly is a row-major
+// [limbs x N] slab of uint64 residues; EVALUATION format is the reference's
+// bit-reversed order.
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "openfhe.h"
+#include "utils/utilities-int.h"
+
+using namespace lbcrypto;
+
+namespace {
+
+thread_local std::string g_err;
+
+std::shared_ptr<ILDCRTParams<BigInteger>> make_params(uint32_t N, uint32_t L, const uint64_t* moduli,
+                                                      const uint64_t* roots) {
+    std::vector<NativeInteger> m(L), r(L);
+    for (uint32_t i = 0; i < L; ++i) {
+        m[i] = NativeInteger(moduli[i]);
+        r[i] = NativeInteger(roots[i]);
+    }
+    return std::make_shared<ILDCRTParams<BigInteger>>(2 * N, m, r);
+}
+
+DCRTPoly make_poly(const std::shared_ptr<ILDCRTParams<BigInteger>>& params, Format fmt, const uint64_t* data) {
+    DCRTPoly p(params, fmt, true);
+    const uint32_t N = params->GetRingDimension();
+    const uint32_t L = params->GetParams().size();
+    for (uint32_t i = 0; i < L; ++i) {
+        NativePoly t = p.GetElementAtIndex(i);
+        NativeVector v(N, t.GetModulus());
+        for (uint32_t j = 0; j < N; ++j)
+            v[j] = NativeInteger(data[(size_t)i * N + j]);
+        t.SetValues(std::move(v), fmt);
+        p.SetElementAtIndex(i, std::move(t));
+    }
+    return p;
+}
+
+void dump_poly(const DCRTPoly& p, uint64_t* out) {
+    const uint32_t N = p.GetRingDimension();
+    const uint32_t L = p.GetNumOfElements();
+    for (uint32_t i = 0; i < L; ++i) {
+        const auto& v = p.GetElementAtIndex(i).GetValues();
+        for (uint32_t j = 0; j < N; ++j)
+            out[(size_t)i * N + j] = v[j].ConvertToInt<uint64_t>();
+    }
+}
+
+struct CkksCtx {
+    CryptoContext<DCRTPoly> cc;
+    KeyPair<DCRTPoly> keys;
+    std::shared_ptr<CryptoParametersCKKSRNS> cp;
+    Ciphertext<DCRTPoly> tmpl;  // an honest encryption, used as metadata template
+    uint32_t N, sizeQ, sizeP;
+    // first-l-limb parameter sets
+    std::shared_ptr<ILDCRTParams<BigInteger>> paramsQl(uint32_t sizeQl) const {
+        const auto& ps = cp->GetElementParams()->GetParams();
+        std::vector<NativeInteger> m(sizeQl), r(sizeQl);
+        for (uint32_t i = 0; i < sizeQl; ++i) {
+            m[i] = ps[i]->GetModulus();
+            r[i] = ps[i]->GetRootOfUnity();
+        }
+        return std::make_shared<ILDCRTParams<BigInteger>>(2 * N, m, r);
+    }
+    std::shared_ptr<ILDCRTParams<BigInteger>> paramsQlP(uint32_t sizeQl) const {
+        const auto& ps = cp->GetElementParams()->GetParams();
+        const auto& pp = cp->GetParamsP()->GetParams();
+        std::vector<NativeInteger> m, r;
+        for (uint32_t i = 0; i < sizeQl; ++i) {
+            m.push_back(ps[i]->GetModulus());
+            r.push_back(ps[i]->GetRootOfUnity());
+        }
+        for (auto& p : pp) {
+            m.push_back(p->GetModulus());
+            r.push_back(p->GetRootOfUnity());
+        }
+        return std::make_shared<ILDCRTParams<BigInteger>>(2 * N, m, r);
+    }
+};
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    }
+    catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+void copy_vec(const std::vector<NativeInteger>& v, uint64_t* out) {
+    for (size_t i = 0; i < v.size(); ++i)
+        out[i] = v[i].ConvertToInt<uint64_t>();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() {
+    return g_err.c_str();
+}
+
+void ref_set_threads(int n) {
+    // utils/parallel.h: OpenFHEParallelControls caps every omp region of the reference
+    omp_set_num_threads(n);
+    OpenFHEParallelControls.Enable();
+    OpenFHEParallelControls.SetNumThreads(n);
+}
+int ref_get_threads() {
+    return OpenFHEParallelControls.GetNumThreads();
+}
+
+// ---------------------------------------------------------------- number theory (nbtheory-impl.h)
+uint64_t ref_root_of_unity(uint32_t m, uint64_t q) {
+    return RootOfUnity<NativeInteger>(m, NativeInteger(q)).ConvertToInt<uint64_t>();
+}
+uint64_t ref_first_prime(uint32_t bits, uint64_t m) {
+    return FirstPrime<NativeInteger>(bits, m).ConvertToInt<uint64_t>();
+}
+uint64_t ref_last_prime(uint32_t bits, uint64_t m) {
+    return LastPrime<NativeInteger>(bits, m).ConvertToInt<uint64_t>();
+}
+uint64_t ref_previous_prime(uint64_t q, uint64_t m) {
+    return PreviousPrime<NativeInteger>(NativeInteger(q), m).ConvertToInt<uint64_t>();
+}
+uint64_t ref_next_prime(uint64_t q, uint64_t m) {
+    return NextPrime<NativeInteger>(NativeInteger(q), m).ConvertToInt<uint64_t>();
+}
+
+// ---------------------------------------------------------------- scalar modular arithmetic (ubintnat.h)
+uint64_t ref_modmul_barrett(uint64_t a, uint64_t b, uint64_t q) {
+    NativeInteger Q(q);
+    return NativeInteger(a).ModMulFast(NativeInteger(b), Q, Q.ComputeMu()).ConvertToInt<uint64_t>();
+}
+uint64_t ref_prep_modmul_const(uint64_t w, uint64_t q) {
+    return NativeInteger(w).PrepModMulConst(NativeInteger(q)).ConvertToInt<uint64_t>();
+}
+uint64_t ref_modmul_const(uint64_t x, uint64_t w, uint64_t q) {
+    NativeInteger W(w), Q(q);
+    return NativeInteger(x).ModMulFastConst(W, Q, W.PrepModMulConst(Q)).ConvertToInt<uint64_t>();
+}
+uint64_t ref_barrett128(uint64_t hi, uint64_t lo, uint64_t q) {
+    // utilities-int.h: BarrettUint128ModUint64 with mu = floor(2^128 / q)
+    DoubleNativeInt a  = (DoubleNativeInt(hi) << 64) | lo;
+    DoubleNativeInt mu = (BigInteger(1).LShiftEq(128) / BigInteger(NativeInteger(q))).ConvertToInt<DoubleNativeInt>();
+    return BarrettUint128ModUint64(a, q, mu);
+}
+
+// ---------------------------------------------------------------- NTT (transformnat-impl.h)
+int ref_ntt_fwd(uint64_t q, uint64_t root, uint32_t N, uint64_t* x) {
+    return guarded([&] {
+        NativeVector v(N, NativeInteger(q));
+        for (uint32_t i = 0; i < N; ++i)
+            v[i] = NativeInteger(x[i]);
+        ChineseRemainderTransformFTT<NativeVector>().ForwardTransformToBitReverseInPlace(NativeInteger(root), 2 * N, &v);
+        for (uint32_t i = 0; i < N; ++i)
+            x[i] = v[i].ConvertToInt<uint64_t>();
+    });
+}
+int ref_ntt_inv(uint64_t q, uint64_t root, uint32_t N, uint64_t* x) {
+    return guarded([&] {
+        NativeVector v(N, NativeInteger(q));
+        for (uint32_t i = 0; i < N; ++i)
+            v[i] = NativeInteger(x[i]);
+        ChineseRemainderTransformFTT<NativeVector>().InverseTransformFromBitReverseInPlace(NativeInteger(root), 2 * N,
+                                                                                           &v);
+        for (uint32_t i = 0; i < N; ++i)
+            x[i] = v[i].ConvertToInt<uint64_t>();
+    });
+}
+// the twiddle tables as the reference builds them (a5): T, T', Tinv, Tinv' each length N
+int ref_twiddles(uint64_t q, uint64_t root, uint32_t N, uint64_t* T, uint64_t* Tp, uint64_t* Ti, uint64_t* Tip,
+                 uint64_t* nInv, uint64_t* nInvPrecon) {
+    return guarded([&] {
+        NativeInteger Q(q);
+        ChineseRemainderTransformFTT<NativeVector>().PreCompute(NativeInteger(root), 2 * N, Q);
+        using X       = ChineseRemainderTransformFTT<NativeVector>;
+        const auto& t = X::m_rootOfUnityReverseTableByModulus[Q];
+        const auto& tp = X::m_rootOfUnityPreconReverseTableByModulus[Q];
+        const auto& ti = X::m_rootOfUnityInverseReverseTableByModulus[Q];
+        const auto& tip = X::m_rootOfUnityInversePreconReverseTableByModulus[Q];
+        for (uint32_t i = 0; i < N; ++i) {
+            T[i]   = t[i].ConvertToInt<uint64_t>();
+            Tp[i]  = tp[i].ConvertToInt<uint64_t>();
+            Ti[i]  = ti[i].ConvertToInt<uint64_t>();
+            Tip[i] = tip[i].ConvertToInt<uint64_t>();
+        }
+        uint32_t msb = GetMSB(N - 1);
+        *nInv        = X::m_cycloOrderInverseTableByModulus[Q][msb].ConvertToInt<uint64_t>();
+        *nInvPrecon  = X::m_cycloOrderInversePreconTableByModulus[Q][msb].ConvertToInt<uint64_t>();
+    });
+}
+
+// ---------------------------------------------------------------- DCRTPoly limb-wise ops (dcrtpoly.h / dcrtpoly-impl.h)
+// op: 0 add, 1 sub, 2 mul (Hadamard), 3 negate(a)
+int ref_dcrt_binop(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, int op, const uint64_t* a,
+                   const uint64_t* b, uint64_t* out) {
+    return guarded([&] {
+        auto params = make_params(N, L, moduli, roots);
+        DCRTPoly A  = make_poly(params, Format::EVALUATION, a);
+        if (op == 3) {
+            dump_poly(A.Negate(), out);
+            return;
+        }
+        DCRTPoly B = make_poly(params, Format::EVALUATION, b);
+        if (op == 0)
+            dump_poly(A + B, out);
+        else if (op == 1)
+            dump_poly(A - B, out);
+        else
+            dump_poly(A * B, out);
+    });
+}
+// Times(std::vector<NativeInteger>) : per-limb scalar
+int ref_dcrt_times_scalars(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, const uint64_t* a,
+                           const uint64_t* scalars, uint64_t* out) {
+    return guarded([&] {
+        auto params = make_params(N, L, moduli, roots);
+        DCRTPoly A  = make_poly(params, Format::EVALUATION, a);
+        std::vector<NativeInteger> s(L);
+        for (uint32_t i = 0; i < L; ++i)
+            s[i] = NativeInteger(scalars[i]);
+        dump_poly(A.Times(s), out);
+    });
+}
+int ref_dcrt_switch_format(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, int from_eval,
+                           uint64_t* data) {
+    return guarded([&] {
+        auto params = make_params(N, L, moduli, roots);
+        DCRTPoly A  = make_poly(params, from_eval ? Format::EVALUATION : Format::COEFFICIENT, data);
+        A.SwitchFormat();
+        dump_poly(A, data);
+    });
+}
+int ref_dcrt_automorphism(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, uint32_t k,
+                          const uint64_t* a, uint64_t* out) {
+    return guarded([&] {
+        auto params = make_params(N, L, moduli, roots);
+        DCRTPoly A  = make_poly(params, Format::EVALUATION, a);
+        std::vector<uint32_t> vec(N);
+        PrecomputeAutoMap(N, k, &vec);
+        dump_poly(A.AutomorphismTransform(k, vec), out);
+    });
+}
+int ref_automorphism_map(uint32_t N, uint32_t k, uint32_t* map) {
+    return guarded([&] {
+        std::vector<uint32_t> vec(N);
+        PrecomputeAutoMap(N, k, &vec);
+        std::copy(vec.begin(), vec.end(), map);
+    });
+}
+// NativeVector::SwitchModulus (mubintvecnat.cpp:109-122) on one limb
+int ref_switch_modulus(uint32_t N, uint64_t q_from, uint64_t q_to, uint64_t* x) {
+    return guarded([&] {
+        NativeVector v(N, NativeInteger(q_from));
+        for (uint32_t i = 0; i < N; ++i)
+            v[i] = NativeInteger(x[i]);
+        v.SwitchModulus(NativeInteger(q_to));
+        for (uint32_t i = 0; i < N; ++i)
+            x[i] = v[i].ConvertToInt<uint64_t>();
+    });
+}
+
+// time L-limb DCRTPoly::SwitchFormat round trips (config 5 / bench reference arm); returns seconds per call
+double ref_time_switch_format(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, uint64_t* data,
+                              int reps) {
+    auto params = make_params(N, L, moduli, roots);
+    DCRTPoly A  = make_poly(params, Format::COEFFICIENT, data);
+    A.SwitchFormat();
+    A.SwitchFormat();  // warm twiddle cache
+    auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r)
+        A.SwitchFormat();
+    auto t1 = std::chrono::steady_clock::now();
+    if (A.GetFormat() != Format::COEFFICIENT)
+        A.SwitchFormat();
+    dump_poly(A, data);
+    return std::chrono::duration<double>(t1 - t0).count() / reps;
+}
+
+// ---------------------------------------------------------------- CKKS context (config 2 and friends)
+// scal_tech: 0 FIXEDMANUAL, 1 FIXEDAUTO, 2 FLEXIBLEAUTO, 3 FLEXIBLEAUTOEXT
+void* ref_ckks_create(uint32_t ring_dim, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
+                      int scal_tech) {
+    CkksCtx* h = nullptr;
+    int rc     = guarded([&] {
+        CCParams<CryptoContextCKKSRNS> p;
+        p.SetRingDim(ring_dim);
+        p.SetMultiplicativeDepth(depth);
+        p.SetScalingModSize(scale_bits);
+        p.SetFirstModSize(first_bits);
+        p.SetKeySwitchTechnique(HYBRID);
+        p.SetSecurityLevel(HEStd_NotSet);
+        if (dnum)
+            p.SetNumLargeDigits(dnum);
+        static const ScalingTechnique st[4] = {FIXEDMANUAL, FIXEDAUTO, FLEXIBLEAUTO, FLEXIBLEAUTOEXT};
+        p.SetScalingTechnique(st[scal_tech]);
+        auto cc = GenCryptoContext(p);
+        cc->Enable(PKE);
+        cc->Enable(KEYSWITCH);
+        cc->Enable(LEVELEDSHE);
+        h        = new CkksCtx();
+        h->cc    = cc;
+        h->keys  = cc->KeyGen();
+        cc->EvalMultKeyGen(h->keys.secretKey);
+        h->cp    = std::dynamic_pointer_cast<CryptoParametersCKKSRNS>(cc->GetCryptoParameters());
+        h->N     = cc->GetRingDimension();
+        h->sizeQ = h->cp->GetElementParams()->GetParams().size();
+        h->sizeP = h->cp->GetParamsP()->GetParams().size();
+        std::vector<double> msg(std::min<uint32_t>(8, h->N / 2), 0.25);
+        auto pt  = cc->MakeCKKSPackedPlaintext(msg);
+        h->tmpl  = cc->Encrypt(h->keys.publicKey, pt);
+    });
+    return rc == 0 ? h : nullptr;
+}
+void ref_ckks_destroy(void* hv) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    if (h) {
+        h->cc->ClearEvalMultKeys();
+        h->cc->ClearEvalAutomorphismKeys();
+        delete h;
+    }
+}
+// shape[0..5] = N, sizeQ, sizeP, numPartQ (dnum), numPerPartQ (alpha), scaling technique
+void ref_ckks_shape(void* hv, uint32_t* shape) {
+    auto* h  = static_cast<CkksCtx*>(hv);
+    shape[0] = h->N;
+    shape[1] = h->sizeQ;
+    shape[2] = h->sizeP;
+    shape[3] = h->cp->GetNumPartQ();
+    shape[4] = h->cp->GetNumPerPartQ();
+    shape[5] = (uint32_t)h->cp->GetScalingTechnique();
+}
+// moduli/roots of Q (sizeQ) followed by P (sizeP)
+void ref_ckks_moduli(void* hv, uint64_t* moduli, uint64_t* roots) {
+    auto* h        = static_cast<CkksCtx*>(hv);
+    const auto& ps = h->cp->GetParamsQP()->GetParams();
+    for (size_t i = 0; i < ps.size(); ++i) {
+        moduli[i] = ps[i]->GetModulus().ConvertToInt<uint64_t>();
+        roots[i]  = ps[i]->GetRootOfUnity().ConvertToInt<uint64_t>();
+    }
+}
+
+// ---- table dumpers (rns-cryptoparameters.h getters, a20) -------------------
+void ref_ckks_PInvModq(void* hv, uint64_t* out) {
+    copy_vec(static_cast<CkksCtx*>(hv)->cp->GetPInvModq(), out);
+}
+void ref_ckks_PModq(void* hv, uint64_t* out) {
+    copy_vec(static_cast<CkksCtx*>(hv)->cp->GetPModq(), out);
+}
+void ref_ckks_PHatInvModp(void* hv, uint64_t* out) {
+    copy_vec(static_cast<CkksCtx*>(hv)->cp->GetPHatInvModp(), out);
+}
+// out[j*sizeQ + i] = [P/p_j]_{q_i}
+void ref_ckks_PHatModq(void* hv, uint64_t* out) {
+    auto* h       = static_cast<CkksCtx*>(hv);
+    const auto& t = h->cp->GetPHatModq();
+    for (size_t j = 0; j < t.size(); ++j)
+        copy_vec(t[j], out + j * h->sizeQ);
+}
+// digit `part`, truncated to `digit_size` limbs: out[i], i < digit_size
+void ref_ckks_PartQlHatInvModq(void* hv, uint32_t part, uint32_t digit_size, uint64_t* out) {
+    copy_vec(static_cast<CkksCtx*>(hv)->cp->GetPartQlHatInvModq(part, digit_size - 1), out);
+}
+// level l = sizeQl-1, digit `part`: out[i*sizeCompl + j]; returns sizeCompl; compl_moduli gets the target basis
+uint32_t ref_ckks_PartQlHatModp(void* hv, uint32_t sizeQl, uint32_t part, uint64_t* out, uint64_t* compl_moduli) {
+    auto* h       = static_cast<CkksCtx*>(hv);
+    const auto& t = h->cp->GetPartQlHatModp(sizeQl - 1, part);
+    const auto& c = h->cp->GetParamsComplPartQ(sizeQl - 1, part)->GetParams();
+    uint32_t sc   = c.size();
+    if (out)
+        for (size_t i = 0; i < t.size(); ++i)
+            copy_vec(t[i], out + i * sc);
+    if (compl_moduli)
+        for (uint32_t j = 0; j < sc; ++j)
+            compl_moduli[j] = c[j]->GetModulus().ConvertToInt<uint64_t>();
+    return sc;
+}
+// rescale tables for dropping limb l = sizeQl-1 (rns-cryptoparameters.h:314-345)
+void ref_ckks_rescale_tables(void* hv, uint32_t sizeQl, uint64_t* QlQlInvModqlDivqlModq, uint64_t* qlInvModq) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    copy_vec(h->cp->GetQlQlInvModqlDivqlModq(h->sizeQ - sizeQl), QlQlInvModqlDivqlModq);
+    copy_vec(h->cp->GetqlInvModq(h->sizeQ - sizeQl), qlInvModq);
+}
+
+// ---- keys -----------------------------------------------------------------
+// relinearisation key: a, b each [dnum][sizeQ+sizeP][N], EVALUATION
+int ref_ckks_evalmult_key(void* hv, uint64_t* a, uint64_t* b) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        const auto& ek = h->cc->GetEvalMultKeyVector(h->keys.secretKey->GetKeyTag())[0];
+        const auto& av = ek->GetAVector();
+        const auto& bv = ek->GetBVector();
+        size_t stride  = (size_t)(h->sizeQ + h->sizeP) * h->N;
+        for (size_t j = 0; j < av.size(); ++j) {
+            dump_poly(av[j], a + j * stride);
+            dump_poly(bv[j], b + j * stride);
+        }
+    });
+}
+// rotation key for slot index `index`; returns the automorphism index k (0 on failure)
+uint32_t ref_ckks_rotate_key(void* hv, int32_t index, uint64_t* a, uint64_t* b) {
+    auto* h    = static_cast<CkksCtx*>(hv);
+    uint32_t k = 0;
+    guarded([&] {
+        h->cc->EvalRotateKeyGen(h->keys.secretKey, {index});
+        k              = h->cc->FindAutomorphismIndex(index);
+        const auto& km = h->cc->GetEvalAutomorphismKeyMap(h->keys.secretKey->GetKeyTag());
+        const auto& ek = km.at(k);
+        const auto& av = ek->GetAVector();
+        const auto& bv = ek->GetBVector();
+        size_t stride  = (size_t)(h->sizeQ + h->sizeP) * h->N;
+        for (size_t j = 0; j < av.size(); ++j) {
+            dump_poly(av[j], a + j * stride);
+            dump_poly(bv[j], b + j * stride);
+        }
+    });
+    return k;
+}
+
+// ---- DCRTPoly-level pieces of the key switch on caller-supplied residues ----
+// ModUp of one digit: a10 as called at keyswitch-hybrid.cpp:359-366.  in: [digit_size][N] COEFFICIENT limbs of
+// digit `part` at level sizeQl; out: [sizeCompl][N] COEFFICIENT.
+int ref_ckks_approx_switch_crt_basis_digit(void* hv, uint32_t sizeQl, uint32_t part, const uint64_t* in,
+                                           uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        const uint32_t alpha = h->cp->GetNumPerPartQ();
+        uint32_t digit_size  = std::min(alpha, sizeQl - alpha * part);
+        const auto& pp       = h->cp->GetParamsPartQ(part)->GetParams();
+        std::vector<NativeInteger> m(digit_size), r(digit_size);
+        for (uint32_t i = 0; i < digit_size; ++i) {
+            m[i] = pp[i]->GetModulus();
+            r[i] = pp[i]->GetRootOfUnity();
+        }
+        auto params  = std::make_shared<ILDCRTParams<BigInteger>>(2 * h->N, m, r);
+        DCRTPoly x   = make_poly(params, Format::COEFFICIENT, in);
+        DCRTPoly res = x.ApproxSwitchCRTBasis(
+            h->cp->GetParamsPartQ(part), h->cp->GetParamsComplPartQ(sizeQl - 1, part),
+            h->cp->GetPartQlHatInvModq(part, digit_size - 1), h->cp->GetPartQlHatInvModqPrecon(part, digit_size - 1),
+            h->cp->GetPartQlHatModp(sizeQl - 1, part), h->cp->GetmodComplPartqBarrettMu(sizeQl - 1, part));
+        dump_poly(res, out);
+    });
+}
+// EvalKeySwitchPrecomputeCore (a16): c [sizeQl][N] EVALUATION -> digits [numPartQl][sizeQl+sizeP][N]; returns numPartQl
+int ref_ckks_modup(void* hv, uint32_t sizeQl, const uint64_t* c, uint64_t* digits) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    int n   = -1;
+    guarded([&] {
+        DCRTPoly C  = make_poly(h->paramsQl(sizeQl), Format::EVALUATION, c);
+        auto d      = h->cc->GetScheme()->EvalKeySwitchPrecomputeCore(C, h->cc->GetCryptoParameters());
+        size_t strd = (size_t)(sizeQl + h->sizeP) * h->N;
+        for (size_t j = 0; j < d->size(); ++j)
+            dump_poly((*d)[j], digits + j * strd);
+        n = d->size();
+    });
+    return n;
+}
+// ApproxModDown (a11): in [sizeQl+sizeP][N] EVALUATION -> out [sizeQl][N] EVALUATION
+int ref_ckks_approx_mod_down(void* hv, uint32_t sizeQl, const uint64_t* in, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        DCRTPoly X = make_poly(h->paramsQlP(sizeQl), Format::EVALUATION, in);
+        auto cp    = h->cp;
+        DCRTPoly R = X.ApproxModDown(h->paramsQl(sizeQl), cp->GetParamsP(), cp->GetPInvModq(), cp->GetPInvModqPrecon(),
+                                     cp->GetPHatInvModp(), cp->GetPHatInvModpPrecon(), cp->GetPHatModq(),
+                                     cp->GetModqBarrettMu(), cp->GettInvModp(), cp->GettInvModpPrecon(), 0,
+                                     cp->GettModqPrecon());
+        dump_poly(R, out);
+    });
+}
+// KeySwitchHYBRID::KeySwitchCore (a18) with the relinearisation key: c [sizeQl][N] -> out0,out1 [sizeQl][N]
+int ref_ckks_keyswitch_core(void* hv, uint32_t sizeQl, const uint64_t* c, uint64_t* out0, uint64_t* out1) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        DCRTPoly C     = make_poly(h->paramsQl(sizeQl), Format::EVALUATION, c);
+        const auto& ek = h->cc->GetEvalMultKeyVector(h->keys.secretKey->GetKeyTag())[0];
+        auto ba        = h->cc->GetScheme()->KeySwitchCore(C, ek);
+        dump_poly((*ba)[0], out0);
+        dump_poly((*ba)[1], out1);
+    });
+}
+// DropLastElementAndScale (a14) through the CKKS rescale tables: x [sizeQl][N] EVALUATION -> [sizeQl-1][N]
+int ref_ckks_rescale_poly(void* hv, uint32_t sizeQl, const uint64_t* x, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        DCRTPoly X = make_poly(h->paramsQl(sizeQl), Format::EVALUATION, x);
+        X.DropLastElementAndScale(h->cp->GetQlQlInvModqlDivqlModq(h->sizeQ - sizeQl),
+                                  h->cp->GetqlInvModq(h->sizeQ - sizeQl));
+        dump_poly(X, out);
+    });
+}
+
+// ---- whole-operation calls through the CryptoContext API --------------------
+static Ciphertext<DCRTPoly> make_ct(CkksCtx* h, uint32_t sizeQl, const uint64_t* data, uint32_t n_polys) {
+    auto ct     = h->tmpl->Clone();
+    auto params = h->paramsQl(sizeQl);
+    std::vector<DCRTPoly> el;
+    for (uint32_t k = 0; k < n_polys; ++k)
+        el.push_back(make_poly(params, Format::EVALUATION, data + (size_t)k * sizeQl * h->N));
+    ct->SetElements(std::move(el));
+    ct->SetLevel(h->sizeQ - sizeQl);
+    return ct;
+}
+// cc->EvalMult(ct1, ct2) (a19, cryptocontext.h:1871): ct* = 2 polys x [sizeQl][N]; out = 2 polys x [sizeQl][N].
+// Valid for scaling techniques where EvalMult itself does not rescale its fresh inputs (all four at noiseScaleDeg 1).
+int ref_ckks_evalmult(void* hv, uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a = make_ct(h, sizeQl, ct1, 2);
+        auto b = make_ct(h, sizeQl, ct2, 2);
+        auto c = h->cc->EvalMult(a, b);
+        if (c->GetElements().size() != 2 || c->GetElements()[0].GetNumOfElements() != sizeQl)
+            OPENFHE_THROW("unexpected EvalMult output shape");
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)sizeQl * h->N);
+    });
+}
+// times `reps` calls of cc->EvalMult on the given towers; returns seconds per op (negative on error)
+double ref_ckks_time_evalmult(void* hv, uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, int warmup,
+                              int reps) {
+    auto* h  = static_cast<CkksCtx*>(hv);
+    double s = -1;
+    guarded([&] {
+        auto a = make_ct(h, sizeQl, ct1, 2);
+        auto b = make_ct(h, sizeQl, ct2, 2);
+        for (int i = 0; i < warmup; ++i)
+            auto c = h->cc->EvalMult(a, b);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < reps; ++i)
+            auto c = h->cc->EvalMult(a, b);
+        auto t1 = std::chrono::steady_clock::now();
+        s       = std::chrono::duration<double>(t1 - t0).count() / reps;
+    });
+    return s;
+}
+// cc->Rescale (FIXEDMANUAL) == ModReduce: 2 polys [sizeQl][N] -> 2 polys [sizeQl-1][N]
+int ref_ckks_rescale(void* hv, uint32_t sizeQl, const uint64_t* ct, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a = make_ct(h, sizeQl, ct, 2);
+        a->SetNoiseScaleDeg(2);
+        auto c = h->cc->GetScheme()->ModReduce(a, 1);
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)(sizeQl - 1) * h->N);
+    });
+}
+// cc->EvalRotate(ct, index) (needs ref_ckks_rotate_key(index) first): 2 polys [sizeQl][N] -> same shape
+int ref_ckks_rotate(void* hv, uint32_t sizeQl, int32_t index, const uint64_t* ct, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a = make_ct(h, sizeQl, ct, 2);
+        auto c = h->cc->EvalRotate(a, index);
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)sizeQl * h->N);
+    });
+}
+// honest end-to-end check material: encrypt a real vector, return its towers; decrypt towers back.
+int ref_ckks_encrypt(void* hv, const double* vals, uint32_t n, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        std::vector<double> v(vals, vals + n);
+        auto pt = h->cc->MakeCKKSPackedPlaintext(v);
+        auto ct = h->cc->Encrypt(h->keys.publicKey, pt);
+        dump_poly(ct->GetElements()[0], out);
+        dump_poly(ct->GetElements()[1], out + (size_t)h->sizeQ * h->N);
+    });
+}
+// decrypt 2 polys at level sizeQl whose noiseScaleDeg is `deg` (2 after a multiplication without rescale)
+int ref_ckks_decrypt(void* hv, uint32_t sizeQl, uint32_t deg, const uint64_t* ct, double* vals, uint32_t n) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a = make_ct(h, sizeQl, ct, 2);
+        a->SetNoiseScaleDeg(deg);
+        double sf = h->tmpl->GetScalingFactor();
+        a->SetScalingFactor(deg == 2 ? sf * sf : sf);
+        Plaintext pt;
+        h->cc->Decrypt(h->keys.secretKey, a, &pt);
+        pt->SetLength(n);
+        auto v = pt->GetRealPackedValue();
+        for (uint32_t i = 0; i < n; ++i)
+            vals[i] = v[i];
+    });
+}
+
+}  // extern "C"
