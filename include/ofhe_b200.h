@@ -1,0 +1,164 @@
+/* ofhe_b200.h -- C ABI of libofhe_b200.so: a Blackwell (sm_100a) RNS / NTT polynomial-arithmetic backend for
+ * OpenFHE's DCRTPoly hot path and hybrid key switching.
+ *
+ * The reference (openfhe-development v1.5.1) has NO C ABI for polynomial arithmetic: its boundary is the compile-time
+ * lattice HAL  src/core/include/lattice/hal/dcrtpoly-interface.h:83-85,153-1417  selected in
+ * src/core/include/lattice/hal/lat-backend.h:39-60.  This header is the boundary a `b200::DCRTPolyImpl` HAL class and a
+ * rebound KeySwitchHYBRID call into (INTEGRATION.md shows both bindings).  Each entry point names the reference
+ * function it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - A polynomial is a row-major [limbs x N] slab of uint64 residues in DEVICE memory; limb l holds residues modulo
+ *    the ring modulus with index mod_idx[l].  Format::EVALUATION is the reference's bit-reversed order, so slabs can
+ *    be exchanged with NativeVector storage word for word (mubintvecnat.h:120-130).
+ *  - Every function returns 0 on success, non-zero on failure; ofhe_last_error() gives the message (per thread).
+ *    No C++ exception crosses this boundary (the reference throws lbcrypto::OpenFHEException, utils/exception.h).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on that stream
+ *    unless they take host pointers (suffix _host), which return after the result is on the host.
+ *  - There is NO CPU fallback: without a CUDA device ofhe_ctx_create fails.
+ */
+#ifndef OFHE_B200_H
+#define OFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ofhe_ctx ofhe_ctx;   /* one CUDA device */
+typedef struct ofhe_ring ofhe_ring; /* ring dimension + registered moduli with their device tables */
+typedef struct ofhe_hks ofhe_hks;   /* hybrid key-switch context over a ring: Q, P, digits, per-level tables */
+typedef struct ofhe_evk ofhe_evk;   /* device-resident evaluation key */
+
+const char* ofhe_last_error(void);
+const char* ofhe_version(void);
+
+/* ---- context / memory ------------------------------------------------------------------------------------------- */
+int ofhe_ctx_create(int device, ofhe_ctx** out);
+void ofhe_ctx_destroy(ofhe_ctx* ctx);
+int ofhe_ctx_sm_count(const ofhe_ctx* ctx);
+int ofhe_malloc(ofhe_ctx* ctx, size_t bytes, void** dptr);
+int ofhe_free(ofhe_ctx* ctx, void* dptr);
+int ofhe_memcpy_h2d(ofhe_ctx* ctx, void* dst_d, const void* src_h, size_t bytes, void* stream);
+int ofhe_memcpy_d2h(ofhe_ctx* ctx, void* dst_h, const void* src_d, size_t bytes, void* stream);
+int ofhe_stream_sync(ofhe_ctx* ctx, void* stream);
+
+/* ---- ring: replaces ILDCRTParams + the static twiddle caches
+ *      ChineseRemainderTransformFTTNat::PreCompute            math/hal/intnat/transformnat-impl.h:714-756
+ *      (moduli/roots as ILDCRTParams holds them, lattice/hal/default/ildcrtparams.h:60-170)                        */
+int ofhe_ring_create(ofhe_ctx* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* moduli_h, const uint64_t* roots_h,
+                     ofhe_ring** out);
+void ofhe_ring_destroy(ofhe_ring* ring);
+/* copies T, T' (forward) and Tinv, Tinv' (inverse) of one modulus to the host, each N words, plus N^-1 and its
+ * Shoup constant: the same six quantities the reference caches per modulus                                        */
+int ofhe_ring_twiddles_host(ofhe_ring* ring, uint32_t mod_idx, uint64_t* T, uint64_t* Tp, uint64_t* Ti, uint64_t* Tip,
+                            uint64_t* nInv, uint64_t* nInvPrecon);
+
+/* ---- a6-a8  DCRTPolyImpl::SwitchFormat                       lattice/hal/default/dcrtpoly-impl.h:1932-1940
+ *             ChineseRemainderTransformFTTNat::ForwardTransformToBitReverseInPlace   transformnat-impl.h:648-658,303-374
+ *             ChineseRemainderTransformFTTNat::InverseTransformFromBitReverseInPlace transformnat-impl.h:678-691,512-625
+ * in -> out (may be the same slab); COEFFICIENT -> EVALUATION (fwd) or back (inv)                                 */
+int ofhe_ntt_fwd(ofhe_ring* ring, const uint64_t* in_d, uint64_t* out_d, uint32_t n_limbs, const uint32_t* mod_idx_h,
+                 void* stream);
+int ofhe_ntt_inv(ofhe_ring* ring, const uint64_t* in_d, uint64_t* out_d, uint32_t n_limbs, const uint32_t* mod_idx_h,
+                 void* stream);
+
+/* ---- a9  DCRTPolyImpl::Plus / Minus / Times / Negate (+ the Eq forms)   lattice/hal/default/dcrtpoly.h:130-190,
+ *          dcrtpoly-impl.h:347-621;  op: 0 add, 1 sub, 2 mul, 3 negate(a), 4 dst += a*b.  dst may alias a or b.   */
+int ofhe_ew_binop(ofhe_ring* ring, int op, uint64_t* dst_d, const uint64_t* a_d, const uint64_t* b_d, uint32_t n_limbs,
+                  const uint32_t* mod_idx_h, void* stream);
+/*          DCRTPolyImpl::Times(const std::vector<NativeInteger>&)          dcrtpoly-impl.h:553-567                */
+int ofhe_ew_mul_scalars(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* a_d, const uint64_t* scalars_h,
+                        uint32_t n_limbs, const uint32_t* mod_idx_h, void* stream);
+/* ---- a4  NativeVectorT::SwitchModulus on one limb               math/hal/intnat/mubintvecnat.cpp:109-122        */
+int ofhe_switch_modulus(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t from_idx, uint32_t to_idx,
+                        void* stream);
+/* ---- a15 DCRTPolyImpl::AutomorphismTransform(k, precomp) (EVALUATION)     dcrtpoly-impl.h:325-333,
+ *          poly-impl.h:366-376, PrecomputeAutoMap core/lib/math/nbtheory2.cpp:264-275 (map built on the device)    */
+int ofhe_automorphism(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t n_limbs, uint32_t k,
+                      void* stream);
+int ofhe_automorphism_map_host(ofhe_ring* ring, uint32_t k, uint32_t* map_h);
+
+/* ---- a10 DCRTPolyImpl::ApproxSwitchCRTBasis                                 dcrtpoly-impl.h:888-932
+ * generic source basis {src_idx} -> target basis {dst_idx} (QHatInvModq / QHatModp are derived from the moduli);
+ * in_d [n_src][N] COEFFICIENT -> out_d [n_dst][N] COEFFICIENT                                                      */
+int ofhe_approx_switch_crt_basis(ofhe_ring* ring, uint32_t n_src, const uint32_t* src_idx_h, uint32_t n_dst,
+                                 const uint32_t* dst_idx_h, const uint64_t* in_d, uint64_t* out_d, void* stream);
+
+/* ---- hybrid key switching.  The ring must hold Q at indices [0,sizeQ) and P at [sizeQ, sizeQ+sizeP).
+ *      Tables: CryptoParametersRNS::PrecomputeCRTTables      pke/lib/schemerns/rns-cryptoparameters.cpp:48-401
+ *              CryptoParametersCKKSRNS::PrecomputeCRTTables  pke/lib/scheme/ckksrns/ckksrns-cryptoparameters.cpp:44-160 */
+int ofhe_hks_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeP, uint32_t numPartQ, ofhe_hks** out);
+void ofhe_hks_destroy(ofhe_hks* hks);
+uint32_t ofhe_hks_num_per_part(const ofhe_hks* hks); /* alpha = GetNumPerPartQ()  rns-cryptoparameters.h:401 */
+/* table read-back for parity checks against the reference getters (rns-cryptoparameters.h:314-560).
+ * which: 0 PInvModq[sizeQ]  1 PModq[sizeQ]  2 PHatInvModp[sizeP]  3 PHatModq[sizeP][sizeQ]
+ *        4 PartQlHatInvModq(part=a, digit_size=b)[b]   5 PartQlHatModp(sizeQl=a, part=b)[digit][compl]
+ *        6 QlQlInvModqlDivqlModq(sizeQl=a)[a-1]        7 qlInvModq(sizeQl=a)[a-1]
+ * returns the number of words written (or needed when out_h is NULL) through *n_words                              */
+int ofhe_hks_table_host(ofhe_hks* hks, int which, uint32_t a, uint32_t b, uint64_t* out_h, size_t* n_words);
+
+/* evaluation key upload: a_h, b_h are [dnum][sizeQ+sizeP][N] EVALUATION (EvalKeyRelinImpl A / B vectors,
+ * pke/include/key/evalkeyrelin.h:141-171)                                                                          */
+int ofhe_evk_create(ofhe_hks* hks, const uint64_t* a_h, const uint64_t* b_h, ofhe_evk** out);
+/* synthetic key of uniform residues generated on the device (benchmarks: throughput does not depend on the values)  */
+int ofhe_evk_create_random(ofhe_hks* hks, uint64_t seed, ofhe_evk** out);
+void ofhe_evk_destroy(ofhe_evk* evk);
+
+/* a16 KeySwitchHYBRID::EvalKeySwitchPrecomputeCore              pke/lib/keyswitch/keyswitch-hybrid.cpp:314-379
+ *     c_d [sizeQl][N] EVALUATION -> digits_d [numPartQl][sizeQl+sizeP][N] EVALUATION                                */
+int ofhe_hks_modup(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* c_d, uint64_t* digits_d, void* stream);
+uint32_t ofhe_hks_num_digits(const ofhe_hks* hks, uint32_t sizeQl);
+/* a17 KeySwitchHYBRID::EvalFastKeySwitchCoreExt                 keyswitch-hybrid.cpp:402-435
+ *     -> e01_d [2][sizeQl+sizeP][N]  (element 0 pairs with the key's B vector, element 1 with A)                    */
+int ofhe_hks_inner_product(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* digits_d, const ofhe_evk* evk,
+                           uint64_t* e01_d, void* stream);
+/* a11 DCRTPolyImpl::ApproxModDown (t = 0, CKKS)                  dcrtpoly-impl.h:966-1005, on n_polys polynomials
+ *     in_d [n_polys][sizeQl+sizeP][N] -> out_d [n_polys][sizeQl][N];  n_polys must be 1 or 2                         */
+int ofhe_hks_approx_mod_down(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_d, uint64_t* out_d, uint32_t n_polys,
+                             void* stream);
+/* a18 KeySwitchHYBRID::KeySwitchCore                             keyswitch-hybrid.cpp:308-312,381-400
+ *     c_d [sizeQl][N] -> out01_d [2][sizeQl][N]                                                                     */
+int ofhe_hks_keyswitch_core(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* c_d, const ofhe_evk* evk,
+                            uint64_t* out01_d, void* stream);
+
+/* a19 CryptoContextImpl::EvalMult(ct1, ct2) = EvalMultCore + relinearise
+ *     pke/include/cryptocontext.h:1871-1879, pke/lib/schemebase/base-leveledshe.cpp:202-214,608-646
+ *     ct*_d [2][sizeQl][N] -> out_d [2][sizeQl][N]  (out_d must not alias the inputs)                               */
+int ofhe_ckks_evalmult(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_d, const uint64_t* ct2_d,
+                       const ofhe_evk* evk, uint64_t* out_d, void* stream);
+/*     same operation on HOST buffers: copies the inputs to the device, runs, copies the result back, synchronises.  */
+int ofhe_ckks_evalmult_host(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_h, const uint64_t* ct2_h,
+                            const ofhe_evk* evk, uint64_t* out_h);
+/* a14 DCRTPolyImpl::DropLastElementAndScale over n_polys polynomials (CKKS rescale)
+ *     dcrtpoly-impl.h:693-712, pke/lib/scheme/ckksrns/ckksrns-leveledshe.cpp:172-191
+ *     in_d [n_polys][sizeQl][N] -> out_d [n_polys][sizeQl-1][N]                                                     */
+int ofhe_ckks_rescale(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_d, uint64_t* out_d, uint32_t n_polys,
+                      void* stream);
+/* a15+a18 LeveledSHEBase::EvalAutomorphism (EvalRotate)          pke/lib/schemebase/base-leveledshe.cpp:382-422
+ *     ct_d [2][sizeQl][N], automorphism index k (FindAutomorphismIndex2nComplex, nbtheory2.cpp:243-262)             */
+int ofhe_ckks_rotate(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, const uint64_t* ct_d, const ofhe_evk* evk,
+                     uint64_t* out_d, void* stream);
+uint32_t ofhe_find_automorphism_index(int32_t index, uint32_t m);
+
+/* ---- a20 (host helper, setup time) CKKS modulus chain + auxiliary primes with the reference's selection rules
+ *      ParameterGenerationCKKSRNS::SinglePrimeModuliGen  pke/lib/scheme/ckksrns/ckksrns-parametergeneration.cpp:409-518
+ *      scal_tech: 0 FIXEDMANUAL 1 FIXEDAUTO 2 FLEXIBLEAUTO.  shape_out: sizeQ, sizeP, dnum, alpha.
+ *      moduli_out / roots_out need room for (depth + 1) + 64 words.                                                */
+int ofhe_ckks_paramgen(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
+                       int scal_tech, uint64_t* moduli_out, uint64_t* roots_out, uint32_t* shape_out);
+uint64_t ofhe_root_of_unity(uint64_t m, uint64_t q);         /* RootOfUnity   nbtheory-impl.h:183-231 */
+uint64_t ofhe_first_prime(uint32_t bits, uint64_t m);        /* FirstPrime    nbtheory-impl.h:329-347 */
+uint64_t ofhe_last_prime(uint32_t bits, uint64_t m);         /* LastPrime     :349-373 */
+uint64_t ofhe_previous_prime(uint64_t q, uint64_t m);        /* PreviousPrime :385-393 */
+uint64_t ofhe_next_prime(uint64_t q, uint64_t m);            /* NextPrime     :375-383 */
+
+/* fills dst_d [n_limbs][N] with uniform residues in [0, q_l) from a counter-based generator (synthetic inputs) */
+int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFHE_B200_H */

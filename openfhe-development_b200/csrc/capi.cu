@@ -1,0 +1,594 @@
+// capi.cu -- the extern "C" boundary declared in include/ofhe_b200.h.  No C++ exception crosses it.
+#include <cstring>
+#include <string>
+
+#include "../../include/ofhe_b200.h"
+#include "hks.h"
+#include "hostmath.h"
+
+using namespace ofhe;
+
+struct ofhe_ctx {
+    Context* c;
+};
+struct ofhe_ring {
+    Ring* r;
+    std::map<std::string, std::unique_ptr<BConv>> bconv_cache;
+    std::mutex mu;
+};
+struct ofhe_hks {
+    Hks* h;
+    ofhe_ring* ring;
+    // pinned staging + device buffers of the *_host entry points (allocated on first use)
+    uint64_t* stage_d = nullptr;
+    size_t stage_words = 0;
+};
+struct ofhe_evk {
+    EvalKey* k;
+};
+
+namespace {
+thread_local std::string g_err;
+
+template <typename F>
+int guard(F&& f) {
+    try {
+        f();
+        return 0;
+    }
+    catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+    catch (...) {
+        g_err = "unknown error";
+        return 1;
+    }
+}
+inline cudaStream_t S(void* s) {
+    return static_cast<cudaStream_t>(s);
+}
+void use(const Ring* r) {
+    OFHE_CUDA(cudaSetDevice(r->ctx->device));
+}
+
+__global__ void fill_uniform_kernel(RingDev r, uint64_t* dst, LimbMap lm, uint64_t seed) {
+    const uint32_t limb = blockIdx.y;
+    const uint64_t q    = r.mc[lm.idx[limb]].q;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < r.N; i += (size_t)gridDim.x * blockDim.x) {
+        // splitmix64 of (seed, limb, i), then the high word of z*q: uniform on [0,q) up to 2^-64 bias
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)limb << 32) + i + 1);
+        z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        dst[(size_t)limb * r.N + i] = __umul64hi(z, q);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* ofhe_last_error(void) {
+    return g_err.c_str();
+}
+const char* ofhe_version(void) {
+    return "ofhe_b200 0.1 (sm_100a)";
+}
+
+int ofhe_ctx_create(int device, ofhe_ctx** out) {
+    return guard([&] {
+        OFHE_REQUIRE(out, "null output pointer");
+        *out = new ofhe_ctx{context_create(device)};
+    });
+}
+void ofhe_ctx_destroy(ofhe_ctx* ctx) {
+    if (ctx) {
+        delete ctx->c;
+        delete ctx;
+    }
+}
+int ofhe_ctx_sm_count(const ofhe_ctx* ctx) {
+    return ctx ? ctx->c->sm_count : 0;
+}
+int ofhe_malloc(ofhe_ctx* ctx, size_t bytes, void** dptr) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaMalloc(dptr, bytes));
+    });
+}
+int ofhe_free(ofhe_ctx* ctx, void* dptr) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaFree(dptr));
+    });
+}
+int ofhe_memcpy_h2d(ofhe_ctx* ctx, void* d, const void* h, size_t bytes, void* stream) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, S(stream)));
+    });
+}
+int ofhe_memcpy_d2h(ofhe_ctx* ctx, void* h, const void* d, size_t bytes, void* stream) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    });
+}
+int ofhe_stream_sync(ofhe_ctx* ctx, void* stream) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaStreamSynchronize(S(stream)));
+    });
+}
+
+int ofhe_ring_create(ofhe_ctx* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* moduli_h, const uint64_t* roots_h,
+                     ofhe_ring** out) {
+    return guard([&] {
+        OFHE_REQUIRE(ctx && moduli_h && roots_h && out, "null argument");
+        auto* h = new ofhe_ring();
+        try {
+            h->r = ring_create(ctx->c, N, n_moduli, moduli_h, roots_h);
+        }
+        catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+void ofhe_ring_destroy(ofhe_ring* ring) {
+    if (ring) {
+        ring->bconv_cache.clear();
+        delete ring->r;
+        delete ring;
+    }
+}
+int ofhe_ring_twiddles_host(ofhe_ring* ring, uint32_t mi, uint64_t* T, uint64_t* Tp, uint64_t* Ti, uint64_t* Tip,
+                            uint64_t* nInv, uint64_t* nInvPrecon) {
+    return guard([&] {
+        Ring* r = ring->r;
+        use(r);
+        OFHE_REQUIRE(mi < r->n_moduli, "modulus index out of range");
+        std::vector<Twiddle> f(r->N), v(r->N);
+        OFHE_CUDA(cudaMemcpy(f.data(), r->tw_fwd_d + (size_t)mi * r->N, sizeof(Twiddle) * r->N, cudaMemcpyDeviceToHost));
+        OFHE_CUDA(cudaMemcpy(v.data(), r->tw_inv_d + (size_t)mi * r->N, sizeof(Twiddle) * r->N, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < r->N; ++i) {
+            T[i]   = f[i].w;
+            Tp[i]  = f[i].ws;
+            Ti[i]  = v[i].w;
+            Tip[i] = v[i].ws;
+        }
+        *nInv       = r->mc_h[mi].nInv;
+        *nInvPrecon = r->mc_h[mi].nInvS;
+    });
+}
+
+static LimbMap checked_map(const Ring* r, uint32_t n, const uint32_t* idx) {
+    OFHE_REQUIRE(idx, "null modulus index list");
+    for (uint32_t i = 0; i < n; ++i)
+        OFHE_REQUIRE(idx[i] < r->n_moduli, "modulus index out of range");
+    return make_map(idx, n);
+}
+
+int ofhe_ntt_fwd(ofhe_ring* ring, const uint64_t* in_d, uint64_t* out_d, uint32_t n_limbs, const uint32_t* mod_idx_h,
+                 void* stream) {
+    return guard([&] {
+        use(ring->r);
+        launch_ntt_fwd(*ring->r, in_d, out_d, checked_map(ring->r, n_limbs, mod_idx_h), S(stream));
+    });
+}
+int ofhe_ntt_inv(ofhe_ring* ring, const uint64_t* in_d, uint64_t* out_d, uint32_t n_limbs, const uint32_t* mod_idx_h,
+                 void* stream) {
+    return guard([&] {
+        use(ring->r);
+        launch_ntt_inv(*ring->r, in_d, out_d, checked_map(ring->r, n_limbs, mod_idx_h), S(stream));
+    });
+}
+int ofhe_ew_binop(ofhe_ring* ring, int op, uint64_t* dst_d, const uint64_t* a_d, const uint64_t* b_d, uint32_t n_limbs,
+                  const uint32_t* mod_idx_h, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE(op >= 0 && op <= 4, "unknown element-wise op");
+        launch_ew(*ring->r, (EwOp)op, dst_d, a_d, b_d, checked_map(ring->r, n_limbs, mod_idx_h), S(stream));
+    });
+}
+int ofhe_ew_mul_scalars(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* a_d, const uint64_t* scalars_h,
+                        uint32_t n_limbs, const uint32_t* mod_idx_h, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        LimbMap lm = checked_map(ring->r, n_limbs, mod_idx_h);
+        ScalarVec sv;
+        for (uint32_t i = 0; i < n_limbs; ++i) {
+            uint64_t q = ring->r->moduli[mod_idx_h[i]];
+            sv.s[i]    = scalars_h[i] % q;  // Times() reduces the scalar first (mubintvecnat.cpp:295-304)
+            sv.ss[i]   = hm::shoup_const(sv.s[i], q);
+        }
+        launch_mul_scalars(*ring->r, dst_d, a_d, sv, lm, S(stream));
+    });
+}
+int ofhe_switch_modulus(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t from_idx, uint32_t to_idx,
+                        void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE(from_idx < ring->r->n_moduli, "modulus index out of range");
+        LimbMap lm = checked_map(ring->r, 1, &to_idx);
+        ScalarVec sv;
+        sv.s[0]  = 1;
+        sv.ss[0] = hm::shoup_const(1, ring->r->moduli[to_idx]);
+        launch_switch_modulus_scale(*ring->r, dst_d, src_d, from_idx, sv, lm, S(stream));
+    });
+}
+int ofhe_automorphism(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t n_limbs, uint32_t k,
+                      void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE((k & 1) && k < 2 * ring->r->N, "automorphism index must be odd and below 2N");
+        OFHE_REQUIRE(dst_d != src_d, "automorphism cannot run in place");
+        launch_automorphism(*ring->r, dst_d, src_d, ring_automap(ring->r, k, S(stream)), n_limbs, S(stream));
+    });
+}
+int ofhe_automorphism_map_host(ofhe_ring* ring, uint32_t k, uint32_t* map_h) {
+    return guard([&] {
+        use(ring->r);
+        const uint32_t* d = ring_automap(ring->r, k, nullptr);
+        OFHE_CUDA(cudaMemcpy(map_h, d, sizeof(uint32_t) * ring->r->N, cudaMemcpyDeviceToHost));
+    });
+}
+
+namespace {
+std::unique_ptr<BConv> build_bconv(const Ring& r, uint32_t n_src, const uint32_t* src, uint32_t n_dst,
+                                   const uint32_t* dst);
+}
+
+int ofhe_approx_switch_crt_basis(ofhe_ring* ring, uint32_t n_src, const uint32_t* src_idx_h, uint32_t n_dst,
+                                 const uint32_t* dst_idx_h, const uint64_t* in_d, uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        checked_map(ring->r, n_src, src_idx_h);
+        checked_map(ring->r, n_dst, dst_idx_h);
+        std::string key((const char*)src_idx_h, n_src * 4);
+        key.push_back('|');
+        key.append((const char*)dst_idx_h, n_dst * 4);
+        BConv* t = nullptr;
+        {
+            std::lock_guard<std::mutex> g(ring->mu);
+            auto it = ring->bconv_cache.find(key);
+            if (it == ring->bconv_cache.end())
+                it = ring->bconv_cache.emplace(key, build_bconv(*ring->r, n_src, src_idx_h, n_dst, dst_idx_h)).first;
+            t = it->second.get();
+        }
+        launch_bconv(*ring->r, *t, in_d, out_d, 1, 0, 0, S(stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ hybrid key switch
+int ofhe_hks_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeP, uint32_t numPartQ, ofhe_hks** out) {
+    return guard([&] {
+        OFHE_REQUIRE(ring && out, "null argument");
+        use(ring->r);
+        auto* h = new ofhe_hks();
+        try {
+            h->h = new Hks(ring->r, sizeQ, sizeP, numPartQ);
+        }
+        catch (...) {
+            delete h;
+            throw;
+        }
+        h->ring = ring;
+        *out    = h;
+    });
+}
+void ofhe_hks_destroy(ofhe_hks* hks) {
+    if (hks) {
+        if (hks->stage_d)
+            cudaFree(hks->stage_d);
+        delete hks->h;
+        delete hks;
+    }
+}
+uint32_t ofhe_hks_num_per_part(const ofhe_hks* hks) {
+    return hks->h->alpha;
+}
+uint32_t ofhe_hks_num_digits(const ofhe_hks* hks, uint32_t sizeQl) {
+    return std::min((sizeQl + hks->h->alpha - 1) / hks->h->alpha, hks->h->dnum);
+}
+
+int ofhe_hks_table_host(ofhe_hks* hks, int which, uint32_t a, uint32_t b, uint64_t* out, size_t* n_words) {
+    return guard([&] {
+        Hks& h        = *hks->h;
+        const Ring& r = *h.ring;
+        const uint64_t* Q = r.moduli.data();
+        const uint64_t* P = Q + h.sizeQ;
+        std::vector<uint64_t> v;
+        switch (which) {
+            case 0: v = h.PInvModq; break;
+            case 1: v = h.PModq; break;
+            case 2:
+                for (uint32_t j = 0; j < h.sizeP; ++j)
+                    v.push_back(hm::inv(hm::prod_mod(P, h.sizeP, j, P[j]), P[j]));
+                break;
+            case 3:
+                for (uint32_t j = 0; j < h.sizeP; ++j)
+                    for (uint32_t i = 0; i < h.sizeQ; ++i)
+                        v.push_back(hm::prod_mod(P, h.sizeP, j, Q[i]));
+                break;
+            case 4: {  // digit a truncated to b limbs
+                OFHE_REQUIRE(a < h.dnum && b >= 1 && a * h.alpha + b <= h.sizeQ, "bad digit");
+                const uint64_t* d = Q + a * h.alpha;
+                for (uint32_t i = 0; i < b; ++i)
+                    v.push_back(hm::inv(hm::prod_mod(d, b, i, d[i]), d[i]));
+                break;
+            }
+            case 5: {  // sizeQl = a, part = b: [digit_size][sizeCompl], complementary basis order
+                OFHE_REQUIRE(a >= 1 && a <= h.sizeQ && b * h.alpha < a, "bad level / digit");
+                uint32_t s = b * h.alpha, ds = std::min(h.alpha, a - s);
+                for (uint32_t i = 0; i < ds; ++i) {
+                    for (uint32_t k = 0; k < a; ++k)
+                        if (k < s || k >= s + ds)
+                            v.push_back(hm::prod_mod(Q + s, ds, i, Q[k]));
+                    for (uint32_t j = 0; j < h.sizeP; ++j)
+                        v.push_back(hm::prod_mod(Q + s, ds, i, P[j]));
+                }
+                break;
+            }
+            case 6:
+            case 7: {
+                OFHE_REQUIRE(a >= 2 && a <= h.sizeQ, "bad level");
+                Hks::Level& lv = h.level(a);
+                for (uint32_t i = 0; i + 1 < a; ++i)
+                    v.push_back(which == 6 ? lv.rescaleA.s[i] : lv.rescaleB.s[i]);
+                break;
+            }
+            default: throw Error("unknown table id");
+        }
+        if (out)
+            std::memcpy(out, v.data(), v.size() * sizeof(uint64_t));
+        if (n_words)
+            *n_words = v.size();
+    });
+}
+
+int ofhe_evk_create(ofhe_hks* hks, const uint64_t* a_h, const uint64_t* b_h, ofhe_evk** out) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        size_t words = (size_t)h.dnum * (h.sizeQ + h.sizeP) * h.ring->N;
+        auto k       = std::make_unique<EvalKey>();
+        k->hks       = &h;
+        k->dnum      = h.dnum;
+        OFHE_CUDA(cudaMalloc(&k->a_d, words * sizeof(uint64_t)));
+        OFHE_CUDA(cudaMalloc(&k->b_d, words * sizeof(uint64_t)));
+        OFHE_CUDA(cudaMemcpy(k->a_d, a_h, words * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        OFHE_CUDA(cudaMemcpy(k->b_d, b_h, words * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        *out = new ofhe_evk{k.release()};
+    });
+}
+int ofhe_evk_create_random(ofhe_hks* hks, uint64_t seed, ofhe_evk** out) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        const uint32_t qp = h.sizeQ + h.sizeP;
+        size_t words      = (size_t)h.dnum * qp * h.ring->N;
+        auto k            = std::make_unique<EvalKey>();
+        k->hks            = &h;
+        k->dnum           = h.dnum;
+        OFHE_CUDA(cudaMalloc(&k->a_d, words * sizeof(uint64_t)));
+        OFHE_CUDA(cudaMalloc(&k->b_d, words * sizeof(uint64_t)));
+        std::vector<uint32_t> idx(qp);
+        for (uint32_t i = 0; i < qp; ++i)
+            idx[i] = i;
+        LimbMap lm = make_map(idx.data(), qp);
+        for (uint32_t j = 0; j < h.dnum; ++j) {
+            dim3 g(64, qp);
+            fill_uniform_kernel<<<g, 256>>>(h.ring->dev(), k->a_d + (size_t)j * qp * h.ring->N, lm, seed + 2 * j);
+            fill_uniform_kernel<<<g, 256>>>(h.ring->dev(), k->b_d + (size_t)j * qp * h.ring->N, lm, seed + 2 * j + 1);
+        }
+        OFHE_CUDA(cudaGetLastError());
+        OFHE_CUDA(cudaDeviceSynchronize());
+        *out = new ofhe_evk{k.release()};
+    });
+}
+void ofhe_evk_destroy(ofhe_evk* evk) {
+    if (evk) {
+        delete evk->k;
+        delete evk;
+    }
+}
+
+int ofhe_hks_modup(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* c_d, uint64_t* digits_d, void* stream) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        uint64_t* tmp = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl)));
+        h.modup(sizeQl, c_d, digits_d, tmp, S(stream));
+    });
+}
+int ofhe_hks_inner_product(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* digits_d, const ofhe_evk* evk,
+                           uint64_t* e01_d, void* stream) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        h.inner_product(sizeQl, ofhe_hks_num_digits(hks, sizeQl), digits_d, *evk->k, e01_d, S(stream));
+    });
+}
+int ofhe_hks_approx_mod_down(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_d, uint64_t* out_d, uint32_t n_polys,
+                             void* stream) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        OFHE_REQUIRE(n_polys == 1 || n_polys == 2, "n_polys must be 1 or 2");
+        const size_t N = h.ring->N, sizeQlP = sizeQl + h.sizeP;
+        uint64_t* ws = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl)));
+        if (n_polys == 2) {
+            h.mod_down2(sizeQl, in_d, out_d, nullptr, ws, ws + 2 * (size_t)h.sizeP * N, S(stream));
+        }
+        else {
+            // run the 2-polynomial pipeline on a duplicated input and keep the first result
+            uint64_t* e01  = ws;
+            uint64_t* o01  = e01 + 2 * sizeQlP * N;
+            uint64_t* ptmp = o01 + 2 * (size_t)sizeQl * N;
+            uint64_t* conv = ptmp + 2 * (size_t)h.sizeP * N;
+            for (int b = 0; b < 2; ++b)
+                OFHE_CUDA(cudaMemcpyAsync(e01 + b * sizeQlP * N, in_d, sizeof(uint64_t) * sizeQlP * N,
+                                          cudaMemcpyDeviceToDevice, S(stream)));
+            h.mod_down2(sizeQl, e01, o01, nullptr, ptmp, conv, S(stream));
+            OFHE_CUDA(cudaMemcpyAsync(out_d, o01, sizeof(uint64_t) * sizeQl * N, cudaMemcpyDeviceToDevice, S(stream)));
+        }
+    });
+}
+int ofhe_hks_keyswitch_core(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* c_d, const ofhe_evk* evk,
+                            uint64_t* out01_d, void* stream) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        uint64_t* ws = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl)));
+        h.keyswitch_core(sizeQl, c_d, *evk->k, out01_d, nullptr, ws, S(stream));
+    });
+}
+int ofhe_ckks_evalmult(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_d, const uint64_t* ct2_d,
+                       const ofhe_evk* evk, uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(hks->h->ring);
+        hks->h->evalmult(sizeQl, ct1_d, ct2_d, *evk->k, out_d, S(stream));
+    });
+}
+int ofhe_ckks_evalmult_host(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_h, const uint64_t* ct2_h,
+                            const ofhe_evk* evk, uint64_t* out_h) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        const size_t words = 2 * (size_t)sizeQl * h.ring->N;
+        if (hks->stage_words < 3 * words) {
+            if (hks->stage_d) {
+                OFHE_CUDA(cudaDeviceSynchronize());
+                OFHE_CUDA(cudaFree(hks->stage_d));
+                hks->stage_d = nullptr;
+            }
+            OFHE_CUDA(cudaMalloc(&hks->stage_d, 3 * words * sizeof(uint64_t)));
+            hks->stage_words = 3 * words;
+        }
+        uint64_t *d1 = hks->stage_d, *d2 = d1 + words, *d3 = d2 + words;
+        cudaStream_t st = nullptr;
+        OFHE_CUDA(cudaMemcpyAsync(d1, ct1_h, words * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        OFHE_CUDA(cudaMemcpyAsync(d2, ct2_h, words * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        h.evalmult(sizeQl, d1, d2, *evk->k, d3, st);
+        OFHE_CUDA(cudaMemcpyAsync(out_h, d3, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        OFHE_CUDA(cudaStreamSynchronize(st));
+    });
+}
+int ofhe_ckks_rescale(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_d, uint64_t* out_d, uint32_t n_polys,
+                      void* stream) {
+    return guard([&] {
+        use(hks->h->ring);
+        hks->h->rescale(sizeQl, in_d, out_d, n_polys, S(stream));
+    });
+}
+int ofhe_ckks_rotate(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, const uint64_t* ct_d, const ofhe_evk* evk,
+                     uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(hks->h->ring);
+        OFHE_REQUIRE((k & 1) && k < 2 * hks->h->ring->N, "automorphism index must be odd and below 2N");
+        hks->h->rotate(sizeQl, k, ct_d, *evk->k, out_d, S(stream));
+    });
+}
+uint32_t ofhe_find_automorphism_index(int32_t index, uint32_t m) {
+    // FindAutomorphismIndex2nComplex (core/lib/math/nbtheory2.cpp:243-262): 5^index mod m (5^-1 for negative index)
+    if (index == 0)
+        return 1;
+    if (index == (int32_t)m - 1)
+        return (uint32_t)index;
+    uint64_t g0 = 5;
+    if (index < 0) {
+        // inverse of 5 modulo the power of two m
+        uint64_t x = 1;
+        for (int i = 0; i < 6; ++i)
+            x = x * (2 - 5 * x);
+        g0 = x & (m - 1);
+    }
+    uint64_t g  = g0;
+    uint32_t n  = (uint32_t)(index < 0 ? -index : index);
+    for (uint32_t j = 1; j < n; ++j)
+        g = (g * g0) & (m - 1);
+    return (uint32_t)g;
+}
+
+int ofhe_ckks_paramgen(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
+                       int scal_tech, uint64_t* moduli_out, uint64_t* roots_out, uint32_t* shape_out) {
+    return guard([&] {
+        OFHE_REQUIRE(scale_bits <= 60 && first_bits <= 60 && scale_bits >= 14, "modulus sizes must be in [14, 60] bits");
+        hm::CkksChain c = hm::ckks_chain(N, depth, scale_bits, first_bits, dnum, scal_tech);
+        std::memcpy(moduli_out, c.moduli.data(), c.moduli.size() * sizeof(uint64_t));
+        std::memcpy(roots_out, c.roots.data(), c.roots.size() * sizeof(uint64_t));
+        shape_out[0] = c.sizeQ;
+        shape_out[1] = c.sizeP;
+        shape_out[2] = c.dnum;
+        shape_out[3] = c.alpha;
+    });
+}
+uint64_t ofhe_root_of_unity(uint64_t m, uint64_t q) {
+    uint64_t r = 0;
+    guard([&] { r = hm::minimal_root_of_unity(m, q); });
+    return r;
+}
+uint64_t ofhe_first_prime(uint32_t bits, uint64_t m) {
+    return hm::first_prime(bits, m);
+}
+uint64_t ofhe_last_prime(uint32_t bits, uint64_t m) {
+    uint64_t r = 0;
+    guard([&] { r = hm::last_prime(bits, m); });
+    return r;
+}
+uint64_t ofhe_previous_prime(uint64_t q, uint64_t m) {
+    return hm::previous_prime(q, m);
+}
+uint64_t ofhe_next_prime(uint64_t q, uint64_t m) {
+    return hm::next_prime(q, m);
+}
+
+int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
+                      void* stream) {
+    return guard([&] {
+        use(ring->r);
+        LimbMap lm = checked_map(ring->r, n_limbs, mod_idx_h);
+        if (n_limbs == 0)
+            return;
+        dim3 g(std::max(1u, std::min(64u, ring->r->N / 256)), n_limbs);
+        fill_uniform_kernel<<<g, 256, 0, S(stream)>>>(ring->r->dev(), dst_d, lm, seed);
+        OFHE_CUDA(cudaGetLastError());
+    });
+}
+
+}  // extern "C"
+
+namespace {
+std::unique_ptr<BConv> build_bconv(const Ring& r, uint32_t n_src, const uint32_t* src, uint32_t n_dst,
+                                   const uint32_t* dst) {
+    OFHE_REQUIRE(n_src >= 1 && n_src <= 64 && n_dst >= 1 && n_dst <= (uint32_t)kMaxLimbs,
+                 "base conversion: unsupported basis size");
+    std::vector<uint64_t> q(n_src);
+    for (uint32_t i = 0; i < n_src; ++i)
+        q[i] = r.moduli[src[i]];
+    std::vector<uint64_t> hinv(2 * (size_t)n_src);
+    std::vector<uint32_t> mat(2 * (size_t)n_src * n_dst);
+    for (uint32_t i = 0; i < n_src; ++i) {
+        uint64_t w      = hm::inv(hm::prod_mod(q.data(), n_src, i, q[i]), q[i]);
+        hinv[2 * i]     = w;
+        hinv[2 * i + 1] = hm::shoup_const(w, q[i]);
+        for (uint32_t j = 0; j < n_dst; ++j) {
+            uint64_t m                         = hm::prod_mod(q.data(), n_src, i, r.moduli[dst[j]]);
+            mat[2 * ((size_t)i * n_dst + j)]     = (uint32_t)(m & ((1u << 30) - 1));
+            mat[2 * ((size_t)i * n_dst + j) + 1] = (uint32_t)(m >> 30);
+        }
+    }
+    auto t   = std::make_unique<BConv>();
+    t->sizeQ = n_src;
+    t->sizeP = n_dst;
+    t->qmap  = make_map(src, n_src);
+    t->pmap  = make_map(dst, n_dst);
+    OFHE_CUDA(cudaMalloc(&t->qhatinv_d, sizeof(uint64_t) * hinv.size()));
+    OFHE_CUDA(cudaMalloc(&t->mat_d, sizeof(uint32_t) * mat.size()));
+    OFHE_CUDA(cudaMemcpy(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size(), cudaMemcpyHostToDevice));
+    OFHE_CUDA(cudaMemcpy(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size(), cudaMemcpyHostToDevice));
+    return t;
+}
+}  // namespace

@@ -1,0 +1,313 @@
+// hks.cu -- hybrid key switching (ModUp -> evk inner product -> ModDown), CKKS EvalMult / rescale / rotation,
+// composed from the kernels of ntt.cu / baseconv.cu / elementwise.cu on device-resident slabs.
+//
+// Device-side replacement for
+//   KeySwitchHYBRID::EvalKeySwitchPrecomputeCore   pke/lib/keyswitch/keyswitch-hybrid.cpp:314-379   (ModUp)
+//   KeySwitchHYBRID::EvalFastKeySwitchCoreExt      :402-435                                          (inner product)
+//   KeySwitchHYBRID::EvalFastKeySwitchCore / KeySwitchCore / KeySwitchInPlace   :381-400,308-312,199-214
+//   DCRTPolyImpl::ApproxModDown                    core/include/lattice/hal/default/dcrtpoly-impl.h:966-1005
+//   DCRTPolyImpl::DropLastElementAndScale          dcrtpoly-impl.h:693-712
+//   LeveledSHEBase::EvalMult / EvalMultCore / EvalAutomorphism   pke/lib/schemebase/base-leveledshe.cpp:202-214,
+//                                                                608-646,382-422
+// and for the table construction of CryptoParametersRNS::PrecomputeCRTTables
+// (pke/lib/schemerns/rns-cryptoparameters.cpp:199-349) and CryptoParametersCKKSRNS::PrecomputeCRTTables
+// (pke/lib/scheme/ckksrns/ckksrns-cryptoparameters.cpp:60-83): every table is a function of the moduli alone and
+// is rebuilt here with word-size modular arithmetic, then kept on the device.
+#include <memory>
+
+#include "hks.h"
+#include "hostmath.h"
+
+namespace ofhe {
+
+namespace {
+
+std::unique_ptr<BConv> make_bconv(const Ring& r, const std::vector<uint32_t>& src_idx,
+                                  const std::vector<uint32_t>& src_pos, const std::vector<uint32_t>& dst_idx,
+                                  const std::vector<uint32_t>& dst_pos) {
+    // source basis {q_i}: QHatInv_i = (prod_{k != i} q_k)^-1 mod q_i;  matrix M[i][j] = prod_{k != i} q_k mod p_j
+    const size_t nq = src_idx.size(), np = dst_idx.size();
+    OFHE_REQUIRE(nq >= 1 && nq <= 64 && np <= (size_t)kMaxLimbs, "base conversion: unsupported basis size");
+    std::vector<uint64_t> q(nq), p(np);
+    for (size_t i = 0; i < nq; ++i)
+        q[i] = r.moduli[src_idx[i]];
+    for (size_t j = 0; j < np; ++j)
+        p[j] = r.moduli[dst_idx[j]];
+    std::vector<uint64_t> hinv(2 * nq);
+    std::vector<uint32_t> mat(2 * nq * np);
+    for (size_t i = 0; i < nq; ++i) {
+        uint64_t w      = hm::inv(hm::prod_mod(q.data(), nq, (long)i, q[i]), q[i]);
+        hinv[2 * i]     = w;
+        hinv[2 * i + 1] = hm::shoup_const(w, q[i]);
+        for (size_t j = 0; j < np; ++j) {
+            uint64_t m               = hm::prod_mod(q.data(), nq, (long)i, p[j]);
+            mat[2 * (i * np + j)]     = (uint32_t)(m & ((1u << 30) - 1));
+            mat[2 * (i * np + j) + 1] = (uint32_t)(m >> 30);
+        }
+    }
+    auto t   = std::make_unique<BConv>();
+    t->sizeQ = (uint32_t)nq;
+    t->sizeP = (uint32_t)np;
+    t->qmap.n = (uint32_t)nq;
+    t->pmap.n = (uint32_t)np;
+    for (size_t i = 0; i < nq; ++i) {
+        t->qmap.idx[i] = (uint16_t)src_idx[i];
+        t->qmap.pos[i] = (uint16_t)src_pos[i];
+    }
+    for (size_t j = 0; j < np; ++j) {
+        t->pmap.idx[j] = (uint16_t)dst_idx[j];
+        t->pmap.pos[j] = (uint16_t)dst_pos[j];
+    }
+    OFHE_CUDA(cudaMalloc(&t->qhatinv_d, sizeof(uint64_t) * hinv.size()));
+    OFHE_CUDA(cudaMalloc(&t->mat_d, sizeof(uint32_t) * mat.size()));
+    OFHE_CUDA(cudaMemcpy(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size(), cudaMemcpyHostToDevice));
+    OFHE_CUDA(cudaMemcpy(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size(), cudaMemcpyHostToDevice));
+    return t;
+}
+
+void fill_scalar(ScalarVec& sv, uint32_t i, uint64_t s, uint64_t q) {
+    sv.s[i]  = s;
+    sv.ss[i] = hm::shoup_const(s, q);
+}
+
+}  // namespace
+
+Hks::Hks(Ring* r, uint32_t sizeQ_, uint32_t sizeP_, uint32_t dnum_) : ring(r), sizeQ(sizeQ_), sizeP(sizeP_), dnum(dnum_) {
+    OFHE_REQUIRE(sizeQ >= 1 && dnum >= 1 && sizeQ + sizeP <= r->n_moduli, "hks: Q and P must be registered in the ring");
+    OFHE_REQUIRE(sizeQ + sizeP <= 128, "hks: at most 128 limbs in QP");
+    alpha = (sizeQ + dnum - 1) / dnum;  // rns-cryptoparameters.cpp:86-95
+    OFHE_REQUIRE(sizeQ > alpha * (dnum - 1), "hks: cannot distribute the towers into the requested number of digits");
+    OFHE_REQUIRE(alpha <= 64, "hks: digits above 64 limbs are not supported");
+    // [P]_{q_i}, [P^-1]_{q_i}  (rns-cryptoparameters.cpp:199-212)
+    const uint64_t* P = r->moduli.data() + sizeQ;
+    PModq.resize(sizeQ);
+    PInvModq.resize(sizeQ);
+    for (uint32_t i = 0; i < sizeQ; ++i) {
+        uint64_t q  = r->moduli[i];
+        PModq[i]    = hm::prod_mod(P, sizeP, -1, q);
+        PInvModq[i] = sizeP ? hm::inv(PModq[i], q) : 1;
+    }
+}
+Hks::~Hks() = default;
+
+Hks::Level& Hks::level(uint32_t sizeQl) {
+    OFHE_REQUIRE(sizeQl >= 1 && sizeQl <= sizeQ, "hks: level out of range");
+    std::lock_guard<std::mutex> g(mu);
+    auto it = levels.find(sizeQl);
+    if (it != levels.end())
+        return *it->second;
+    OFHE_CUDA(cudaSetDevice(ring->ctx->device));
+    auto lv        = std::make_unique<Level>();
+    const Ring& r  = *ring;
+    const uint32_t sizeQlP = sizeQl + sizeP;
+    lv->n_digits   = std::min((sizeQl + alpha - 1) / alpha, dnum);  // keyswitch-hybrid.cpp:327-329
+    // modulus index of row i of a Ql.P slab
+    std::vector<uint32_t> qlp(sizeQlP);
+    for (uint32_t i = 0; i < sizeQlP; ++i)
+        qlp[i] = i < sizeQl ? i : sizeQ + (i - sizeQl);
+    lv->map_QlP = make_map(qlp.data(), sizeQlP);
+    lv->map_Ql  = make_map(qlp.data(), sizeQl);
+    // ---- ModUp: digit j converts rows [j*alpha, j*alpha+ds) of the INTT'd input into all the other rows of its own
+    //      Ql.P slab (complementary partition, rns-cryptoparameters.cpp:252-294, written in place: no assembly copy)
+    lv->map_modup_ntt.n = 0;
+    for (uint32_t j = 0; j < lv->n_digits; ++j) {
+        const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
+        std::vector<uint32_t> si, sp, di, dp;
+        for (uint32_t i = 0; i < ds; ++i) {
+            si.push_back(s + i);
+            sp.push_back(s + i);  // row in the [sizeQl][N] coefficient-format copy of c
+        }
+        for (uint32_t i = 0; i < sizeQlP; ++i)
+            if (i < s || i >= s + ds) {
+                di.push_back(qlp[i]);
+                dp.push_back(i);  // row in digit j's own [sizeQlP][N] slab
+                uint32_t n                  = lv->map_modup_ntt.n++;
+                OFHE_REQUIRE(n < (uint32_t)kMaxLimbs && j * sizeQlP + i < 65536, "hks: ModUp exceeds the per-launch limb capacity");
+                lv->map_modup_ntt.idx[n] = (uint16_t)qlp[i];
+                lv->map_modup_ntt.pos[n] = (uint16_t)(j * sizeQlP + i);
+            }
+        lv->modup.push_back(make_bconv(r, si, sp, di, dp));
+    }
+    // ---- ModDown: P rows -> Ql rows  (PHatInvModp / PHatModq, rns-cryptoparameters.cpp:214-229)
+    if (sizeP) {
+        std::vector<uint32_t> si, sp, di, dp;
+        for (uint32_t j = 0; j < sizeP; ++j) {
+            si.push_back(sizeQ + j);
+            sp.push_back(j);
+        }
+        for (uint32_t i = 0; i < sizeQl; ++i) {
+            di.push_back(i);
+            dp.push_back(i);
+        }
+        lv->moddown = make_bconv(r, si, sp, di, dp);
+    }
+    // two-polynomial maps used by the batched ModDown
+    lv->map_P2.n = 0;
+    lv->map_Ql2.n = 0;
+    for (uint32_t b = 0; b < 2; ++b) {
+        for (uint32_t j = 0; j < sizeP; ++j) {
+            uint32_t n        = lv->map_P2.n++;
+            lv->map_P2.idx[n] = (uint16_t)(sizeQ + j);
+            lv->map_P2.pos[n] = (uint16_t)(b * sizeQlP + sizeQl + j);  // P rows of e_b inside [2][sizeQlP][N]
+        }
+        for (uint32_t i = 0; i < sizeQl; ++i) {
+            uint32_t n         = lv->map_Ql2.n++;
+            lv->map_Ql2.idx[n] = (uint16_t)i;
+            lv->map_Ql2.pos[n] = (uint16_t)(b * sizeQl + i);
+            fill_scalar(lv->pinv2, b * sizeQl + i, PInvModq[i], r.moduli[i]);
+        }
+    }
+    // ---- CKKS rescale constants for dropping limb l = sizeQl-1 (ckksrns-cryptoparameters.cpp:60-83):
+    //      A_i = floor(QlInv * Ql / q_l) mod q_i = -q_l^-1 mod q_i (q_i | Ql),  B_i = q_l^-1 mod q_i
+    if (sizeQl >= 2) {
+        const uint32_t l = sizeQl - 1;
+        for (uint32_t i = 0; i < l; ++i) {
+            uint64_t qi = r.moduli[i], B = hm::inv(r.moduli[l] % qi, qi);
+            fill_scalar(lv->rescaleA, i, qi - B, qi);
+            fill_scalar(lv->rescaleB, i, B, qi);
+        }
+    }
+    auto& ref = *lv;
+    levels[sizeQl] = std::move(lv);
+    return ref;
+}
+
+size_t Hks::workspace_words(uint32_t sizeQl) const {
+    const size_t N = ring->N, sizeQlP = sizeQl + sizeP;
+    //  coeff copy of c | digits | e0,e1 | P rows (coefficient format) of e0,e1 | converted Ql rows of both | c2
+    return N * ((size_t)sizeQl + (size_t)dnum * sizeQlP + 2 * sizeQlP + 2 * sizeP + 2 * (size_t)sizeQl + sizeQl);
+}
+
+void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, sizeQlP = sizeQl + sizeP;
+    // 1. all digits at once: coefficient-format copy of c                            (keyswitch-hybrid.cpp:359)
+    launch_ntt_inv(r, c, coeff_tmp, lv.map_Ql, st);
+    for (uint32_t j = 0; j < lv.n_digits; ++j) {
+        uint64_t* D      = digits + (size_t)j * sizeQlP * N;
+        const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
+        // 2. fast base conversion straight into the complementary rows of D_j           (:360-365)
+        launch_bconv(r, *lv.modup[j], coeff_tmp, D, 1, 0, 0, st);
+        // 3. the digit's own rows keep the ORIGINAL evaluation-format limbs of c          (:372-373)
+        OFHE_CUDA(cudaMemcpyAsync(D + (size_t)s * N, c + (size_t)s * N, sizeof(uint64_t) * ds * N,
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+    // 4. one launch transforms every converted row of every digit back to EVALUATION      (:366)
+    launch_ntt_fwd(r, digits, digits, lv.map_modup_ntt, st);
+}
+
+void Hks::inner_product(uint32_t sizeQl, uint32_t n_digits, const uint64_t* digits, const EvalKey& evk, uint64_t* e01,
+                        cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, sizeQlP = sizeQl + sizeP, sizeQP = sizeQ + sizeP;
+    OFHE_REQUIRE(evk.hks == this, "evaluation key belongs to a different key-switch context");
+    OFHE_REQUIRE(n_digits <= evk.dnum, "more digits than the evaluation key holds");
+    launch_ks_inner_product(r, n_digits, digits, sizeQlP * N, evk.a_d, evk.b_d, sizeQP * N, sizeQl, sizeQ - sizeQl, e01,
+                            e01 + sizeQlP * N, lv.map_QlP, st);
+}
+
+void Hks::mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const uint64_t* addend01, uint64_t* p_tmp,
+                    uint64_t* conv_tmp, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, sizeQlP = sizeQl + sizeP;
+    OFHE_REQUIRE(sizeP >= 1, "ModDown needs a non-empty auxiliary basis");
+    // P rows of both polynomials -> coefficient format, gathered into p_tmp [2][sizeP][N]   (dcrtpoly-impl.h:976-984)
+    PosMap gather;
+    for (uint32_t n = 0; n < lv.map_P2.n; ++n)
+        gather.pos[n] = (uint16_t)n;
+    launch_ntt_inv(r, e01, p_tmp, lv.map_P2, st, &gather);
+    // P -> Ql conversion of both polynomials in one launch                                     (:987-988)
+    launch_bconv(r, *lv.moddown, p_tmp, conv_tmp, 2, (size_t)sizeP * N, (size_t)sizeQl * N, st);
+    // back to EVALUATION                                                                         (:1001)
+    launch_ntt_fwd(r, conv_tmp, conv_tmp, lv.map_Ql2, st);
+    // out = (e - conv) * P^-1 (+ addend)                                                          (:1002)
+    for (uint32_t b = 0; b < 2; ++b) {
+        ScalarVec sv;
+        for (uint32_t i = 0; i < sizeQl; ++i) {
+            sv.s[i]  = lv.pinv2.s[i];
+            sv.ss[i] = lv.pinv2.ss[i];
+        }
+        launch_sub_mul_scalars(r, out01 + (size_t)b * sizeQl * N, e01 + (size_t)b * sizeQlP * N,
+                               conv_tmp + (size_t)b * sizeQl * N, sv,
+                               addend01 ? addend01 + (size_t)b * sizeQl * N : nullptr, lv.map_Ql, st);
+    }
+}
+
+void Hks::keyswitch_core(uint32_t sizeQl, const uint64_t* c, const EvalKey& evk, uint64_t* out01,
+                         const uint64_t* addend01, uint64_t* ws, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const size_t N = ring->N, sizeQlP = sizeQl + sizeP;
+    uint64_t* coeff  = ws;
+    uint64_t* digits = coeff + (size_t)sizeQl * N;
+    uint64_t* e01    = digits + (size_t)dnum * sizeQlP * N;
+    uint64_t* p_tmp  = e01 + 2 * sizeQlP * N;
+    uint64_t* conv   = p_tmp + 2 * (size_t)sizeP * N;
+    modup(sizeQl, c, digits, coeff, st);
+    inner_product(sizeQl, lv.n_digits, digits, evk, e01, st);
+    mod_down2(sizeQl, e01, out01, addend01, p_tmp, conv, st);
+}
+
+void Hks::evalmult(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, const EvalKey& evk, uint64_t* out,
+                   cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, P = (size_t)sizeQl * N;
+    uint64_t* ws = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * workspace_words(sizeQl)));
+    uint64_t* c2 = ws + (workspace_words(sizeQl) - P);
+    // tensor product: out = (c0, c1), c2 to scratch                                     (base-leveledshe.cpp:620-624)
+    launch_tensor(r, ct1, ct1 + P, ct2, ct2 + P, out, out + P, c2, lv.map_Ql, st);
+    // relinearise: (c0, c1) += KeySwitchCore(c2)                                          (base-leveledshe.cpp:207-211)
+    keyswitch_core(sizeQl, c2, evk, out, out, ws, st);
+}
+
+void Hks::rescale(uint32_t sizeQl, const uint64_t* in, uint64_t* out, uint32_t n_polys, cudaStream_t st) {
+    OFHE_REQUIRE(sizeQl >= 2, "rescale needs at least two limbs");
+    Level& lv      = level(sizeQl);
+    Level& lvm     = level(sizeQl - 1);
+    const Ring& r  = *ring;
+    const size_t N = r.N;
+    const uint32_t l = sizeQl - 1;
+    uint64_t* ws   = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * N * (1 + (size_t)l)));
+    uint64_t* z    = ws;
+    uint64_t* t    = ws + N;
+    uint32_t last  = l;
+    LimbMap one    = make_map(&last, 1);
+    for (uint32_t k = 0; k < n_polys; ++k) {
+        const uint64_t* x = in + (size_t)k * sizeQl * N;
+        uint64_t* o       = out + (size_t)k * l * N;
+        one.pos[0]        = 0;
+        launch_ntt_inv(r, x + (size_t)l * N, z, one, st);                       // dcrtpoly-impl.h:696-697
+        launch_switch_modulus_scale(r, t, z, l, lv.rescaleA, lvm.map_Ql, st);   // :703-704
+        launch_ntt_fwd(r, t, t, lvm.map_Ql, st);                                // :705-706
+        launch_mul_scalars_add(r, o, x, lv.rescaleB, t, lvm.map_Ql, st);        // :707-708
+    }
+}
+
+void Hks::rotate(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const EvalKey& evk, uint64_t* out, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, P = (size_t)sizeQl * N;
+    uint64_t* ws  = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * (workspace_words(sizeQl) + 2 * P)));
+    uint64_t* tmp = ws + workspace_words(sizeQl);
+    // KeySwitchInPlace on a 2-element ciphertext: (c0 + ab0, ab1), ab = KeySwitchCore(c1)   (keyswitch-hybrid.cpp:199-214)
+    // the addend for the second polynomial is absent, so run the two ModDown tails separately via a zeroed addend
+    OFHE_CUDA(cudaMemcpyAsync(tmp, ct, sizeof(uint64_t) * P, cudaMemcpyDeviceToDevice, st));
+    OFHE_CUDA(cudaMemsetAsync(tmp + P, 0, sizeof(uint64_t) * P, st));
+    keyswitch_core(sizeQl, ct + P, evk, tmp, tmp, ws, st);
+    // both polynomials through the automorphism gather                                   (base-leveledshe.cpp:414-420)
+    const uint32_t* map = ring_automap(ring, k, st);
+    launch_automorphism(r, out, tmp, map, 2 * sizeQl, st);
+    (void)lv;
+}
+
+EvalKey::~EvalKey() {
+    if (a_d)
+        cudaFree(a_d);
+    if (b_d)
+        cudaFree(b_d);
+}
+
+}  // namespace ofhe

@@ -1,0 +1,63 @@
+// hks.h -- hybrid key-switch context (device tables per level) and evaluation keys.  See hks.cu.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace ofhe {
+
+struct Hks;
+
+// evaluation key: a_j, b_j for j < dnum, each over the full QP basis, EVALUATION format, device resident
+// (EvalKeyRelinImpl::GetAVector/GetBVector, pke/include/key/evalkeyrelin.h:141-171)
+struct EvalKey {
+    Hks* hks      = nullptr;
+    uint32_t dnum = 0;
+    uint64_t* a_d = nullptr;  // [dnum][sizeQ+sizeP][N]
+    uint64_t* b_d = nullptr;
+    ~EvalKey();
+};
+
+struct Hks {
+    Ring* ring;
+    uint32_t sizeQ, sizeP, dnum, alpha;
+    std::vector<uint64_t> PModq, PInvModq;
+
+    struct Level {
+        uint32_t n_digits = 0;
+        LimbMap map_Ql, map_QlP;
+        LimbMap map_modup_ntt;  // every converted row of every digit slab
+        LimbMap map_P2, map_Ql2;
+        std::vector<std::unique_ptr<BConv>> modup;
+        std::unique_ptr<BConv> moddown;
+        ScalarVec pinv2;
+        ScalarVec rescaleA, rescaleB;
+    };
+    std::map<uint32_t, std::unique_ptr<Level>> levels;
+    std::mutex mu;
+
+    Hks(Ring* r, uint32_t sizeQ, uint32_t sizeP, uint32_t dnum);
+    ~Hks();
+    Level& level(uint32_t sizeQl);
+    size_t workspace_words(uint32_t sizeQl) const;
+
+    // c [sizeQl][N] EVALUATION -> digits [n_digits][sizeQl+sizeP][N] EVALUATION; coeff_tmp [sizeQl][N] scratch
+    void modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st);
+    // e01 [2][sizeQl+sizeP][N]
+    void inner_product(uint32_t sizeQl, uint32_t n_digits, const uint64_t* digits, const EvalKey& evk, uint64_t* e01,
+                       cudaStream_t st);
+    // e01 [2][sizeQl+sizeP][N] -> out01 [2][sizeQl][N] (+ addend01 if given; may alias out01)
+    void mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const uint64_t* addend01, uint64_t* p_tmp,
+                   uint64_t* conv_tmp, cudaStream_t st);
+    void keyswitch_core(uint32_t sizeQl, const uint64_t* c, const EvalKey& evk, uint64_t* out01,
+                        const uint64_t* addend01, uint64_t* ws, cudaStream_t st);
+    void evalmult(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, const EvalKey& evk, uint64_t* out,
+                  cudaStream_t st);
+    void rescale(uint32_t sizeQl, const uint64_t* in, uint64_t* out, uint32_t n_polys, cudaStream_t st);
+    void rotate(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const EvalKey& evk, uint64_t* out, cudaStream_t st);
+};
+
+}  // namespace ofhe

@@ -1,0 +1,149 @@
+// internal.h -- host-side objects behind the opaque C handles of include/ofhe_b200.h, and the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "modarith.cuh"
+
+namespace ofhe {
+
+constexpr int kMaxLimbs = 256;  // limbs per launch (e.g. all dnum x (sizeQl+sizeP) converted limbs of a ModUp)
+
+// limb -> (registered-modulus index, row of the slab), passed by value as a kernel parameter: digits, dropped
+// limbs and the P-extension are metadata-only re-indexings (SURVEY.md 7 hard part 4), never copies.
+struct LimbMap {
+    uint32_t n;
+    uint16_t idx[kMaxLimbs];  // modulus index in the ring
+    uint16_t pos[kMaxLimbs];  // row index: limb data lives at base + pos * N
+};
+
+struct PosMap {  // output rows when a transform writes to a differently laid-out slab
+    uint16_t pos[kMaxLimbs];
+};
+
+// device view of a ring: tables of every registered modulus
+struct RingDev {
+    const ModConst* mc;     // [n_moduli]
+    const Twiddle* tw_fwd;  // [n_moduli][N]  T[brev(i)] = psi^i      (transformnat-impl.h:714-756)
+    const Twiddle* tw_inv;  // [n_moduli][N]  Tinv[brev(i)] = psi^-i
+    uint32_t N;
+    uint32_t logN;
+};
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define OFHE_CUDA(expr)                                                                                     \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            throw ::ofhe::Error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" + \
+                                std::to_string(__LINE__));                                                  \
+    } while (0)
+#define OFHE_REQUIRE(cond, msg)            \
+    do {                                   \
+        if (!(cond))                       \
+            throw ::ofhe::Error(msg);      \
+    } while (0)
+
+struct Context {
+    int device = 0;
+    int sm_count = 0;
+    // scratch arena for the fused pipelines (grown on demand, never shrunk)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+    void* get_scratch(size_t bytes);
+    ~Context();
+};
+
+struct Ring;
+Context* context_create(int device);
+Ring* ring_create(Context* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* moduli, const uint64_t* roots);
+const uint32_t* ring_automap(Ring* r, uint32_t k, cudaStream_t st);
+
+struct Ring {
+    Context* ctx = nullptr;
+    uint32_t N = 0, logN = 0, n_moduli = 0;
+    std::vector<uint64_t> moduli, roots;
+    std::vector<ModConst> mc_h;
+    ModConst* mc_d = nullptr;
+    Twiddle* tw_fwd_d = nullptr;
+    Twiddle* tw_inv_d = nullptr;
+    std::map<uint32_t, uint32_t*> automaps;  // k -> device map (nbtheory2.cpp:264-275)
+    RingDev dev() const { return RingDev{mc_d, tw_fwd_d, tw_inv_d, N, logN}; }
+    ~Ring();
+};
+
+inline LimbMap make_map(const uint32_t* idx, uint32_t n) {
+    OFHE_REQUIRE(n <= (uint32_t)kMaxLimbs, "too many limbs in one call");
+    LimbMap m;
+    m.n = n;
+    for (uint32_t i = 0; i < n; ++i) {
+        m.idx[i] = (uint16_t)idx[i];
+        m.pos[i] = (uint16_t)i;
+    }
+    return m;
+}
+
+// ---- kernel launchers (all asynchronous on `st`) ----------------------------------------------------
+// NTT: in -> out (in == out allowed).  Limb l of the launch lives at base + lm.pos[l] * N in both slabs.
+// If out_pos is given, limb l is read from in + lm.pos[l] * N and written to out + out_pos->pos[l] * N.
+void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
+                    const PosMap* out_pos = nullptr);
+void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
+                    const PosMap* out_pos = nullptr);
+
+enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2, EW_NEG = 3, EW_MAC = 4 /* dst += a*b */ };
+void launch_ew(const Ring& r, EwOp op, uint64_t* dst, const uint64_t* a, const uint64_t* b, const LimbMap& lm,
+               cudaStream_t st);
+// dst = a * scalar[limb]  (+ addend if not null):  DCRTPolyImpl::Times(vector<NativeInteger>)
+struct ScalarVec {
+    uint64_t s[kMaxLimbs];
+    uint64_t ss[kMaxLimbs];  // Shoup constants
+};
+void launch_mul_scalars(const Ring& r, uint64_t* dst, const uint64_t* a, const ScalarVec& sv, const LimbMap& lm,
+                        cudaStream_t st);
+void launch_automorphism(const Ring& r, uint64_t* dst, const uint64_t* src, const uint32_t* map_d, uint32_t n_limbs,
+                         cudaStream_t st);
+void launch_build_automap(uint32_t N, uint32_t logN, uint32_t k, uint32_t* map_d, cudaStream_t st);
+// dst[l] = centred switch of the single limb `src` (modulus index from_idx) into every modulus of lm, times
+// scalar sv[l] (Shoup): the SwitchModulus + scalar multiply of DropLastElementAndScale (dcrtpoly-impl.h:703-705)
+void launch_switch_modulus_scale(const Ring& r, uint64_t* dst, const uint64_t* src, uint32_t from_idx,
+                                 const ScalarVec& sv, const LimbMap& lm, cudaStream_t st);
+// dst = a * s[l] + b   (the tail of DropLastElementAndScale, dcrtpoly-impl.h:708-709)
+void launch_mul_scalars_add(const Ring& r, uint64_t* dst, const uint64_t* a, const ScalarVec& sv, const uint64_t* b,
+                            const LimbMap& lm, cudaStream_t st);
+// dst = (a - b) * s[l] (+ c if c != nullptr)   (the tail of ApproxModDown, dcrtpoly-impl.h:1002, optionally fused
+// with the `cv[k] += ab[k]` of relinearisation, base-leveledshe.cpp:209-210)
+void launch_sub_mul_scalars(const Ring& r, uint64_t* dst, const uint64_t* a, const uint64_t* b, const ScalarVec& sv,
+                            const uint64_t* c, const LimbMap& lm, cudaStream_t st);
+
+// fast base conversion tables (a10), device resident
+struct BConv {
+    uint32_t sizeQ = 0, sizeP = 0;
+    LimbMap qmap, pmap;  // source limbs (rows of `in`) and target limbs (rows of `out`: pos may leave a gap)
+    // device: per source limb QHatInvModq + Shoup constant; matrix QHatModp split in 30-bit halves [sizeQ][sizeP]
+    uint64_t* qhatinv_d = nullptr;   // [sizeQ][2] (w, ws)
+    uint32_t* mat_d = nullptr;       // [sizeQ][sizeP][2] (lo30, hi30)
+    ~BConv();
+};
+// `batch` independent polynomials, `in_stride` / `out_stride` words apart
+void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* out, uint32_t batch, size_t in_stride,
+                  size_t out_stride, cudaStream_t st);
+
+// hybrid key-switch inner product (a17)
+void launch_ks_inner_product(const Ring& r, uint32_t n_digits, const uint64_t* digits, size_t digit_stride,
+                             const uint64_t* evk_a, const uint64_t* evk_b, size_t evk_stride, uint32_t sizeQl,
+                             uint32_t delta, uint64_t* e0, uint64_t* e1, const LimbMap& lm, cudaStream_t st);
+// EvalMultCore tensor (a19): c0=a0*b0, c1=a0*b1+a1*b0, c2=a1*b1
+void launch_tensor(const Ring& r, const uint64_t* a0, const uint64_t* a1, const uint64_t* b0, const uint64_t* b1,
+                   uint64_t* c0, uint64_t* c1, uint64_t* c2, const LimbMap& lm, cudaStream_t st);
+
+}  // namespace ofhe

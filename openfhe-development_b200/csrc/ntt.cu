@@ -1,0 +1,388 @@
+// ntt.cu -- negacyclic NTT / inverse NTT over [limbs x N] slabs of 64-bit residues, sm_100a.
+//
+// Replaces ChineseRemainderTransformFTTNat::{ForwardTransformToBitReverseInPlace,
+// InverseTransformFromBitReverseInPlace} (src/core/include/math/hal/intnat/transformnat-impl.h:303-374,
+// 512-625, 648-691) and the limb loop of DCRTPolyImpl::SwitchFormat (lattice/hal/default/dcrtpoly-impl.h:1932).
+// Same contract: forward = natural order in, bit-reversed order out; inverse = the opposite; canonical
+// residues in [0,q) on exit; twiddle tables T[brev(i)] = psi^i with Shoup constants.
+//
+// B200 decomposition (not the reference's stage-by-stage loop):
+//   forward :  [strided kernel: first logN-12 stages, 2^(logN-12) points per thread, no shared memory]
+//              [tile kernel   : last 12 stages on contiguous 4096-point tiles (32 KiB of shared memory),
+//                               three radix-16 register rounds with two swizzled smem exchanges]
+//   inverse :  the mirror image (tile kernel first, strided kernel last with N^-1 folded in).
+// Butterflies are Harvey-lazy: forward values live in [0,4q), inverse values in [0,2q); one final
+// conditional subtraction makes the output canonical, hence bit-identical to the reference.
+// The intermediate between the two kernels stays L2-resident for slabs that fit the 126 MB L2.
+#include "internal.h"
+
+namespace ofhe {
+
+namespace {
+// NOTE: `in` and `out` may be the same slab (in-place transforms), so data pointers carry no __restrict__.
+
+__device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
+    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    return Twiddle{v.x, v.y};
+}
+
+// Cooley-Tukey butterfly, inputs/outputs in [0,4q)
+__device__ __forceinline__ void ct_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, uint64_t q, uint64_t twoq) {
+    uint64_t x = X >= twoq ? X - twoq : X;
+    uint64_t v = shoup_lazy(Y, t.w, t.ws, q);
+    X          = x + v;
+    Y          = x - v + twoq;
+}
+// Gentleman-Sande butterfly, inputs/outputs in [0,2q)
+__device__ __forceinline__ void gs_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, uint64_t q, uint64_t twoq) {
+    uint64_t s = X + Y;
+    uint64_t d = X - Y + twoq;
+    X          = s >= twoq ? s - twoq : s;
+    Y          = shoup_lazy(d, t.w, t.ws, q);
+}
+
+// One stage (local depth D of R) on 2^R register-resident points; all indices are compile-time constants so the
+// point array stays in registers.  x[k]: local index k, MSB = the round's first stage bit.
+// tw_base = 2^s0 + u (s0 = the round's first global stage, u = the s0 index bits above this group).
+template <int R, int D>
+__device__ __forceinline__ void ct_stage(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                         uint64_t q, uint64_t twoq) {
+    constexpr int half = 1 << (R - 1 - D);
+#pragma unroll
+    for (int g = 0; g < (1 << D); ++g) {
+        const Twiddle t = ld_tw(tw + ((tw_base << D) + g));
+#pragma unroll
+        for (int l = 0; l < half; ++l)
+            ct_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, q, twoq);
+    }
+}
+template <int R, int D>
+__device__ __forceinline__ void gs_stage(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                         uint64_t q, uint64_t twoq) {
+    constexpr int half = 1 << (R - 1 - D);
+#pragma unroll
+    for (int g = 0; g < (1 << D); ++g) {
+        const Twiddle t = ld_tw(tw + ((tw_base << D) + g));
+#pragma unroll
+        for (int l = 0; l < half; ++l)
+            gs_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, q, twoq);
+    }
+}
+// the transform's final inverse stage with N^-1 folded in (transformnat-impl.h:600-624):
+// X = (X+Y)*nInv, Y = (X-Y)*(Tinv[1]*nInv), both canonical
+template <int R>
+__device__ __forceinline__ void gs_last_stage(uint64_t (&x)[1 << R], const ModConst& mc, uint64_t q, uint64_t twoq) {
+    constexpr int half = 1 << (R - 1);
+#pragma unroll
+    for (int l = 0; l < half; ++l) {
+        const uint64_t s = x[l] + x[l + half];
+        const uint64_t e = x[l] - x[l + half] + twoq;
+        x[l]             = shoup(s, mc.nInv, mc.nInvS, q);
+        x[l + half]      = shoup(e, mc.w1nInv, mc.w1nInvS, q);
+    }
+}
+
+// R consecutive CT stages
+template <int R>
+__device__ __forceinline__ void ct_round(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                         uint64_t q, uint64_t twoq) {
+    ct_stage<R, 0>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 1) ct_stage<R, 1>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 2) ct_stage<R, 2>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 3) ct_stage<R, 3>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 4) ct_stage<R, 4>(x, tw, tw_base, q, twoq);
+}
+// R consecutive GS stages (mirror order).  If LAST, local depth 0 is the transform's final stage.
+template <int R, bool LAST>
+__device__ __forceinline__ void gs_round(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                         const ModConst& mc, uint64_t q, uint64_t twoq) {
+    if constexpr (R > 4) gs_stage<R, 4>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 3) gs_stage<R, 3>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 2) gs_stage<R, 2>(x, tw, tw_base, q, twoq);
+    if constexpr (R > 1) gs_stage<R, 1>(x, tw, tw_base, q, twoq);
+    if constexpr (LAST)
+        gs_last_stage<R>(x, mc, q, twoq);
+    else
+        gs_stage<R, 0>(x, tw, tw_base, q, twoq);
+}
+
+__device__ __forceinline__ uint64_t canon4(uint64_t v, uint64_t q, uint64_t twoq) {  // [0,4q) -> [0,q)
+    v = v >= twoq ? v - twoq : v;
+    return v >= q ? v - q : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided kernels: the A = logN - 12 stages whose butterfly span is >= 4096.  One thread owns the 2^A
+// points {c + k * N/2^A}; a warp's loads are 256 contiguous bytes per k.  Twiddles T[1 .. 2^A) are
+// warp-uniform.  No shared memory.
+template <int A>
+__global__ void __launch_bounds__(256) ntt_fwd_strided(RingDev r, const uint64_t* in,
+                                                        uint64_t* out, LimbMap lm, PosMap op) {
+    const uint32_t limb   = blockIdx.y;
+    const uint32_t mi     = lm.idx[limb];
+    const uint32_t stride = r.N >> A;
+    const uint32_t c      = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= stride)
+        return;
+    const uint64_t q = r.mc[mi].q, twoq = 2 * q;
+    const uint64_t* src = in + (size_t)lm.pos[limb] * r.N + c;
+    uint64_t* dst       = out + (size_t)op.pos[limb] * r.N + c;
+    uint64_t x[1 << A];
+#pragma unroll
+    for (int k = 0; k < (1 << A); ++k)
+        x[k] = src[(size_t)k * stride];
+    ct_round<A>(x, r.tw_fwd + (size_t)mi * r.N, 1u, q, twoq);
+#pragma unroll
+    for (int k = 0; k < (1 << A); ++k)
+        dst[(size_t)k * stride] = x[k];  // lazy [0,4q): the tile kernel canonicalises
+}
+
+template <int A>
+__global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data, LimbMap lm) {
+    const uint32_t limb   = blockIdx.y;
+    const uint32_t mi     = lm.idx[limb];
+    const uint32_t stride = r.N >> A;
+    const uint32_t c      = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= stride)
+        return;
+    const ModConst mc = r.mc[mi];
+    const uint64_t q = mc.q, twoq = 2 * q;
+    uint64_t* p = data + (size_t)lm.pos[limb] * r.N + c;
+    uint64_t x[1 << A];
+#pragma unroll
+    for (int k = 0; k < (1 << A); ++k)
+        x[k] = p[(size_t)k * stride];
+    gs_round<A, true>(x, r.tw_inv + (size_t)mi * r.N, 1u, mc, q, twoq);
+    // every point passed through the folded last stage => already canonical
+#pragma unroll
+    for (int k = 0; k < (1 << A); ++k)
+        p[(size_t)k * stride] = x[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile kernels: 12 stages on a contiguous tile of 4096 points, 256 threads x 16 points.
+//   round A: tile bits 11..8   thread t holds c = t + 256k              (coalesced global access)
+//   round B: tile bits  7..4   thread t holds c = (t>>4)*256 + (t&15) + 16k
+//   round C: tile bits  3..0   thread t holds c = 16t + k               (128 contiguous bytes / thread)
+// Exchange A<->B is conflict-free in linear layout; B<->C uses the swizzle c ^ ((c>>4)&15).
+constexpr int kTile = 4096;
+__device__ __forceinline__ uint32_t swz(uint32_t c) {
+    return c ^ ((c >> 4) & 15u);
+}
+
+template <bool SINGLE>  // SINGLE: logN == 12, input is canonical and no strided kernel ran before
+__global__ void __launch_bounds__(256) ntt_fwd_tile(RingDev r, const uint64_t* in,
+                                                     uint64_t* out, LimbMap lm, PosMap op) {
+    __shared__ uint64_t sm[kTile];
+    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+    const uint32_t mi = lm.idx[limb];
+    const uint64_t q = r.mc[mi].q, twoq = 2 * q;
+    const Twiddle* tw   = r.tw_fwd + (size_t)mi * r.N;
+    const uint32_t s0   = r.logN - 12;  // first stage handled here
+    const size_t base   = (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
+    const size_t obase  = (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
+    uint64_t x[16];
+    // ---- round A
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = in[base + t + 256 * k];
+    ct_round<4>(x, tw, (1u << s0) + tile, q, twoq);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[t + 256 * k] = x[k];
+    __syncthreads();
+    // ---- round B
+    const uint32_t bh = t >> 4, bl = t & 15u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[bh * 256 + bl + 16 * k];
+    ct_round<4>(x, tw, ((1u << s0) + tile) * 16u + bh, q, twoq);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[swz(bh * 256 + bl + 16 * k)] = x[k];
+    __syncthreads();
+    // ---- round C
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[swz(16 * t + k)];
+    ct_round<4>(x, tw, ((1u << s0) + tile) * 256u + t, q, twoq);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + obase + 16 * t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        dst[k] = make_ulonglong2(canon4(x[2 * k], q, twoq), canon4(x[2 * k + 1], q, twoq));
+}
+
+template <bool SINGLE>  // SINGLE: logN == 12, the folded last stage happens in round A
+__global__ void __launch_bounds__(256) ntt_inv_tile(RingDev r, const uint64_t* in,
+                                                     uint64_t* out, LimbMap lm, PosMap op) {
+    __shared__ uint64_t sm[kTile];
+    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+    const uint32_t mi = lm.idx[limb];
+    const ModConst mc = r.mc[mi];
+    const uint64_t q = mc.q, twoq = 2 * q;
+    const Twiddle* tw = r.tw_inv + (size_t)mi * r.N;
+    const uint32_t s0 = r.logN - 12;
+    const size_t base = (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
+    const size_t obase = (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
+    uint64_t x[16];
+    // ---- round C (stages logN-1 .. logN-4)
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(in + base + 16 * t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        ulonglong2 v = src[k];
+        x[2 * k]     = v.x;
+        x[2 * k + 1] = v.y;
+    }
+    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 256u + t, mc, q, twoq);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[swz(16 * t + k)] = x[k];
+    __syncthreads();
+    // ---- round B
+    const uint32_t bh = t >> 4, bl = t & 15u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[swz(bh * 256 + bl + 16 * k)];
+    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 16u + bh, mc, q, twoq);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[bh * 256 + bl + 16 * k] = x[k];
+    __syncthreads();
+    // ---- round A
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[t + 256 * k];
+    gs_round<4, SINGLE>(x, tw, (1u << s0) + tile, mc, q, twoq);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        out[obase + t + 256 * k] = x[k];  // SINGLE: canonical; else lazy [0,2q), finished by the strided kernel
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small rings (N < 4096: the reference's unit-test sizes): one CTA per limb, whole limb in shared memory,
+// one stage per barrier.  Not a performance path.
+template <bool INV>
+__global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap lm, PosMap op) {
+    extern __shared__ uint64_t s[];
+    const uint32_t limb = lm.pos[blockIdx.x], olimb = op.pos[blockIdx.x], mi = lm.idx[blockIdx.x], N = r.N;
+    const ModConst mc = r.mc[mi];
+    const uint64_t q = mc.q, twoq = 2 * q;
+    const Twiddle* tw = (INV ? r.tw_inv : r.tw_fwd) + (size_t)mi * N;
+    for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
+        s[i] = in[(size_t)limb * N + i];
+    __syncthreads();
+    if (!INV) {
+        for (uint32_t m = 1, t = N >> 1; m < N; m <<= 1, t >>= 1) {
+            for (uint32_t b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
+                uint32_t i = b / t, j = 2 * i * t + (b % t);
+                ct_bfly(s[j], s[j + t], ld_tw(tw + m + i), q, twoq);
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
+            out[(size_t)olimb * N + i] = canon4(s[i], q, twoq);
+    }
+    else {
+        for (uint32_t m = N >> 1, t = 1; m > 1; m >>= 1, t <<= 1) {
+            for (uint32_t b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
+                uint32_t i = b / t, j = 2 * i * t + (b % t);
+                gs_bfly(s[j], s[j + t], ld_tw(tw + m + i), q, twoq);
+            }
+            __syncthreads();
+        }
+        const uint32_t h = N >> 1;
+        for (uint32_t j = threadIdx.x; j < h; j += blockDim.x) {
+            uint64_t a = s[j] + s[j + h], e = s[j] - s[j + h] + twoq;
+            out[(size_t)olimb * N + j]     = shoup(a, mc.nInv, mc.nInvS, q);
+            out[(size_t)olimb * N + j + h] = shoup(e, mc.w1nInv, mc.w1nInvS, q);
+        }
+    }
+}
+
+// the second kernel of a pair works in place on the OUTPUT slab: same moduli, output rows
+LimbMap on_output(const LimbMap& lm, const PosMap& op) {
+    LimbMap o = lm;
+    for (uint32_t i = 0; i < lm.n; ++i)
+        o.pos[i] = op.pos[i];
+    return o;
+}
+template <int A>
+void fwd_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+    const uint32_t stride = r.N >> A;
+    dim3 g1((stride + 255) / 256, lm.n);
+    ntt_fwd_strided<A><<<g1, 256, 0, st>>>(r.dev(), in, out, lm, op);
+    dim3 g2(r.N / kTile, lm.n);
+    ntt_fwd_tile<false><<<g2, 256, 0, st>>>(r.dev(), out, out, on_output(lm, op), op);
+}
+template <int A>
+void inv_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+    dim3 g2(r.N / kTile, lm.n);
+    ntt_inv_tile<false><<<g2, 256, 0, st>>>(r.dev(), in, out, lm, op);
+    const uint32_t stride = r.N >> A;
+    dim3 g1((stride + 255) / 256, lm.n);
+    ntt_inv_strided<A><<<g1, 256, 0, st>>>(r.dev(), out, on_output(lm, op));
+}
+PosMap default_pos(const LimbMap& lm, const PosMap* out_pos) {
+    if (out_pos)
+        return *out_pos;
+    PosMap p;
+    for (uint32_t i = 0; i < lm.n; ++i)
+        p.pos[i] = lm.pos[i];
+    return p;
+}
+
+}  // namespace
+
+void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
+                    const PosMap* out_pos) {
+    if (lm.n == 0)
+        return;
+    const PosMap op = default_pos(lm, out_pos);
+    if (r.logN < 12) {
+        uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
+        ntt_small<false><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op);
+    }
+    else if (r.logN == 12) {
+        ntt_fwd_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op);
+    }
+    else {
+        switch (r.logN - 12) {
+            case 1: fwd_big<1>(r, in, out, lm, op, st); break;
+            case 2: fwd_big<2>(r, in, out, lm, op, st); break;
+            case 3: fwd_big<3>(r, in, out, lm, op, st); break;
+            case 4: fwd_big<4>(r, in, out, lm, op, st); break;
+            case 5: fwd_big<5>(r, in, out, lm, op, st); break;
+            default: throw Error("ring dimension above 2^17 is not supported");
+        }
+    }
+    OFHE_CUDA(cudaGetLastError());
+}
+
+void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
+                    const PosMap* out_pos) {
+    if (lm.n == 0)
+        return;
+    const PosMap op = default_pos(lm, out_pos);
+    if (r.logN < 12) {
+        uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
+        ntt_small<true><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op);
+    }
+    else if (r.logN == 12) {
+        ntt_inv_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op);
+    }
+    else {
+        switch (r.logN - 12) {
+            case 1: inv_big<1>(r, in, out, lm, op, st); break;
+            case 2: inv_big<2>(r, in, out, lm, op, st); break;
+            case 3: inv_big<3>(r, in, out, lm, op, st); break;
+            case 4: inv_big<4>(r, in, out, lm, op, st); break;
+            case 5: inv_big<5>(r, in, out, lm, op, st); break;
+            default: throw Error("ring dimension above 2^17 is not supported");
+        }
+    }
+    OFHE_CUDA(cudaGetLastError());
+}
+
+}  // namespace ofhe

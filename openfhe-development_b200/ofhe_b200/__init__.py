@@ -1,0 +1,313 @@
+"""ofhe_b200 -- Python (ctypes) binding of libofhe_b200.so, the sm_100a RNS/NTT backend for OpenFHE's DCRTPoly
+hot path.  The binding only marshals pointers: device memory, streams and torch.distributed come from PyTorch
+(plumbing), every arithmetic operation runs in the hand-written CUDA kernels behind include/ofhe_b200.h.
+
+There is NO CPU fallback: importing works anywhere (so the CPU-only test tier can check the ABI), but creating a
+``Context`` without a CUDA device, or with the shared library missing, raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libofhe_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "ofhe_b200.h")
+
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes): mirrors include/ofhe_b200.h one to one (tests/test_abi.py checks the two agree)
+SIGNATURES = {
+    "ofhe_last_error": (C.c_char_p, []),
+    "ofhe_version": (C.c_char_p, []),
+    "ofhe_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ofhe_ctx_destroy": (None, [_vp]),
+    "ofhe_ctx_sm_count": (C.c_int, [_vp]),
+    "ofhe_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "ofhe_free": (C.c_int, [_vp, _vp]),
+    "ofhe_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "ofhe_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "ofhe_stream_sync": (C.c_int, [_vp, _vp]),
+    "ofhe_ring_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp)]),
+    "ofhe_ring_destroy": (None, [_vp]),
+    "ofhe_ring_twiddles_host": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _u64p, _u64p]),
+    "ofhe_ntt_fwd": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "ofhe_ntt_inv": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "ofhe_ew_binop": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "ofhe_ew_mul_scalars": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "ofhe_switch_modulus": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "ofhe_automorphism": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "ofhe_automorphism_map_host": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "ofhe_approx_switch_crt_basis": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_hks_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "ofhe_hks_destroy": (None, [_vp]),
+    "ofhe_hks_num_per_part": (C.c_uint32, [_vp]),
+    "ofhe_hks_num_digits": (C.c_uint32, [_vp, C.c_uint32]),
+    "ofhe_hks_table_host": (C.c_int, [_vp, C.c_int, C.c_uint32, C.c_uint32, _vp, C.POINTER(C.c_size_t)]),
+    "ofhe_evk_create": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "ofhe_evk_create_random": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
+    "ofhe_evk_destroy": (None, [_vp]),
+    "ofhe_hks_modup": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_hks_inner_product": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_hks_approx_mod_down": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp]),
+    "ofhe_hks_keyswitch_core": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_evalmult": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_evalmult_host": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_rescale": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp]),
+    "ofhe_ckks_rotate": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_find_automorphism_index": (C.c_uint32, [C.c_int32, C.c_uint32]),
+    "ofhe_ckks_paramgen": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp,
+                                      _vp]),
+    "ofhe_root_of_unity": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "ofhe_first_prime": (C.c_uint64, [C.c_uint32, C.c_uint64]),
+    "ofhe_last_prime": (C.c_uint64, [C.c_uint32, C.c_uint64]),
+    "ofhe_previous_prime": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "ofhe_next_prime": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "ofhe_fill_uniform": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp]),
+}
+
+_lib = None
+
+
+class OfheError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libofhe_b200.so (built in-tree by `make -C openfhe-development_b200`); fails loudly if missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OfheError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                            "(there is no CPU fallback for this backend)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise OfheError(lib().ofhe_last_error().decode())
+
+
+def _ptr(x):
+    """Device pointer of a torch tensor / raw int; host pointer of a numpy array."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+def _idx(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---- host helpers (setup time, no GPU needed) ---------------------------------------------------------------------
+def ckks_paramgen(N, depth, scale_bits, first_bits, dnum=0, scal_tech=0):
+    """CKKS modulus chain with the reference's selection rules -> dict(moduli, roots, sizeQ, sizeP, dnum, alpha)."""
+    moduli = np.zeros(depth + 1 + 64, dtype=np.uint64)
+    roots = np.zeros_like(moduli)
+    shape = np.zeros(4, dtype=np.uint32)
+    _ck(lib().ofhe_ckks_paramgen(N, depth, scale_bits, first_bits, dnum, scal_tech, moduli.ctypes.data,
+                                 roots.ctypes.data, shape.ctypes.data))
+    sizeQ, sizeP, dn, alpha = (int(v) for v in shape)
+    n = sizeQ + sizeP
+    return dict(N=N, moduli=moduli[:n].copy(), roots=roots[:n].copy(), sizeQ=sizeQ, sizeP=sizeP, dnum=dn, alpha=alpha)
+
+
+def dcrt_params(N, n_limbs, bits):
+    """ILDCRTParams(order, depth, bits) moduli: LastPrime(bits, 2N) then successive PreviousPrime
+    (lattice/hal/default/ildcrtparams.h:100-118), with their minimal roots."""
+    L = lib()
+    m = 2 * N
+    q = [L.ofhe_last_prime(bits, m)]
+    for _ in range(n_limbs - 1):
+        q.append(L.ofhe_previous_prime(q[-1], m))
+    roots = [L.ofhe_root_of_unity(m, x) for x in q]
+    return np.array(q, dtype=np.uint64), np.array(roots, dtype=np.uint64)
+
+
+def find_automorphism_index(index, m):
+    return lib().ofhe_find_automorphism_index(index, m)
+
+
+# ---- device objects -------------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device=0):
+        h = _vp()
+        _ck(lib().ofhe_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    @property
+    def sm_count(self):
+        return lib().ofhe_ctx_sm_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().ofhe_ctx_destroy(self.h)
+            self.h = None
+
+    def zeros(self, *shape):
+        """uint64 slab on this device (torch int64 storage, bit pattern = uint64)."""
+        import torch
+
+        return torch.zeros(*shape, dtype=torch.int64, device=f"cuda:{self.device}")
+
+    def upload(self, arr):
+        import torch
+
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        return torch.from_numpy(a.view(np.int64)).to(f"cuda:{self.device}")
+
+    @staticmethod
+    def download(t):
+        return t.detach().cpu().numpy().view(np.uint64)
+
+
+class Ring:
+    """ILDCRTParams + twiddle tables on the device."""
+
+    def __init__(self, ctx, N, moduli, roots):
+        self.ctx = ctx
+        self.N = int(N)
+        self.moduli = np.ascontiguousarray(moduli, dtype=np.uint64)
+        self.roots = np.ascontiguousarray(roots, dtype=np.uint64)
+        h = _vp()
+        _ck(lib().ofhe_ring_create(ctx.h, self.N, len(self.moduli), self.moduli.ctypes.data, self.roots.ctypes.data,
+                                   C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().ofhe_ring_destroy(self.h)
+            self.h = None
+
+    def twiddles(self, mod_idx):
+        T, Tp, Ti, Tip = (np.empty(self.N, dtype=np.uint64) for _ in range(4))
+        ni, nip = C.c_uint64(), C.c_uint64()
+        _ck(lib().ofhe_ring_twiddles_host(self.h, mod_idx, T.ctypes.data, Tp.ctypes.data, Ti.ctypes.data,
+                                          Tip.ctypes.data, C.byref(ni), C.byref(nip)))
+        return T, Tp, Ti, Tip, ni.value, nip.value
+
+    # DCRTPoly::SwitchFormat pieces
+    def ntt_fwd(self, src, dst, mod_idx):
+        mi = _idx(mod_idx)
+        _ck(lib().ofhe_ntt_fwd(self.h, _ptr(src), _ptr(dst), len(mi), mi.ctypes.data, _stream()))
+
+    def ntt_inv(self, src, dst, mod_idx):
+        mi = _idx(mod_idx)
+        _ck(lib().ofhe_ntt_inv(self.h, _ptr(src), _ptr(dst), len(mi), mi.ctypes.data, _stream()))
+
+    def binop(self, op, dst, a, b, mod_idx):
+        mi = _idx(mod_idx)
+        _ck(lib().ofhe_ew_binop(self.h, op, _ptr(dst), _ptr(a), _ptr(b), len(mi), mi.ctypes.data, _stream()))
+
+    def mul_scalars(self, dst, a, scalars, mod_idx):
+        mi = _idx(mod_idx)
+        s = np.ascontiguousarray(scalars, dtype=np.uint64)
+        _ck(lib().ofhe_ew_mul_scalars(self.h, _ptr(dst), _ptr(a), s.ctypes.data, len(mi), mi.ctypes.data, _stream()))
+
+    def switch_modulus(self, dst, src, from_idx, to_idx):
+        _ck(lib().ofhe_switch_modulus(self.h, _ptr(dst), _ptr(src), from_idx, to_idx, _stream()))
+
+    def automorphism(self, dst, src, n_limbs, k):
+        _ck(lib().ofhe_automorphism(self.h, _ptr(dst), _ptr(src), n_limbs, k, _stream()))
+
+    def automorphism_map(self, k):
+        m = np.empty(self.N, dtype=np.uint32)
+        _ck(lib().ofhe_automorphism_map_host(self.h, k, m.ctypes.data))
+        return m
+
+    def approx_switch_crt_basis(self, src_idx, dst_idx, src, dst):
+        si, di = _idx(src_idx), _idx(dst_idx)
+        _ck(lib().ofhe_approx_switch_crt_basis(self.h, len(si), si.ctypes.data, len(di), di.ctypes.data, _ptr(src),
+                                               _ptr(dst), _stream()))
+
+    def fill_uniform(self, dst, mod_idx, seed):
+        mi = _idx(mod_idx)
+        _ck(lib().ofhe_fill_uniform(self.h, _ptr(dst), len(mi), mi.ctypes.data, seed, _stream()))
+
+
+class EvalKey:
+    def __init__(self, hks, a=None, b=None, seed=None):
+        h = _vp()
+        if a is not None:
+            a = np.ascontiguousarray(a, dtype=np.uint64)
+            b = np.ascontiguousarray(b, dtype=np.uint64)
+            _ck(lib().ofhe_evk_create(hks.h, a.ctypes.data, b.ctypes.data, C.byref(h)))
+        else:
+            _ck(lib().ofhe_evk_create_random(hks.h, 0 if seed is None else seed, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().ofhe_evk_destroy(self.h)
+            self.h = None
+
+
+class Hks:
+    """KeySwitchHYBRID + CryptoParametersRNS tables over a ring whose moduli are [Q | P]."""
+
+    def __init__(self, ring, sizeQ, sizeP, dnum):
+        self.ring = ring
+        self.sizeQ, self.sizeP, self.dnum = int(sizeQ), int(sizeP), int(dnum)
+        h = _vp()
+        _ck(lib().ofhe_hks_create(ring.h, sizeQ, sizeP, dnum, C.byref(h)))
+        self.h = h
+        self.alpha = lib().ofhe_hks_num_per_part(h)
+
+    def close(self):
+        if self.h:
+            lib().ofhe_hks_destroy(self.h)
+            self.h = None
+
+    def num_digits(self, sizeQl):
+        return lib().ofhe_hks_num_digits(self.h, sizeQl)
+
+    def table(self, which, a=0, b=0):
+        n = C.c_size_t()
+        _ck(lib().ofhe_hks_table_host(self.h, which, a, b, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint64)
+        _ck(lib().ofhe_hks_table_host(self.h, which, a, b, out.ctypes.data, C.byref(n)))
+        return out
+
+    def modup(self, sizeQl, c, digits):
+        _ck(lib().ofhe_hks_modup(self.h, sizeQl, _ptr(c), _ptr(digits), _stream()))
+
+    def inner_product(self, sizeQl, digits, evk, e01):
+        _ck(lib().ofhe_hks_inner_product(self.h, sizeQl, _ptr(digits), evk.h, _ptr(e01), _stream()))
+
+    def approx_mod_down(self, sizeQl, src, dst, n_polys=1):
+        _ck(lib().ofhe_hks_approx_mod_down(self.h, sizeQl, _ptr(src), _ptr(dst), n_polys, _stream()))
+
+    def keyswitch_core(self, sizeQl, c, evk, out01):
+        _ck(lib().ofhe_hks_keyswitch_core(self.h, sizeQl, _ptr(c), evk.h, _ptr(out01), _stream()))
+
+    def evalmult(self, sizeQl, ct1, ct2, evk, out):
+        _ck(lib().ofhe_ckks_evalmult(self.h, sizeQl, _ptr(ct1), _ptr(ct2), evk.h, _ptr(out), _stream()))
+
+    def evalmult_host(self, sizeQl, ct1, ct2, evk, out):
+        """numpy (or pinned torch CPU) buffers in, numpy out: host<->device copies included."""
+        _ck(lib().ofhe_ckks_evalmult_host(self.h, sizeQl, _ptr(ct1), _ptr(ct2), evk.h, _ptr(out)))
+
+    def rescale(self, sizeQl, src, dst, n_polys=2):
+        _ck(lib().ofhe_ckks_rescale(self.h, sizeQl, _ptr(src), _ptr(dst), n_polys, _stream()))
+
+    def rotate(self, sizeQl, k, ct, evk, out):
+        _ck(lib().ofhe_ckks_rotate(self.h, sizeQl, k, _ptr(ct), evk.h, _ptr(out), _stream()))

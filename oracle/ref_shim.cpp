@@ -553,13 +553,17 @@ double ref_ckks_time_evalmult(void* hv, uint32_t sizeQl, const uint64_t* ct1, co
     });
     return s;
 }
-// cc->Rescale (FIXEDMANUAL) == ModReduce: 2 polys [sizeQl][N] -> 2 polys [sizeQl-1][N]
+// the rescale every scaling technique ends up in (LeveledSHECKKSRNS::ModReduceInternalInPlace,
+// ckksrns-leveledshe.cpp:172-191; cc->Rescale reaches it directly under FIXEDMANUAL): 2 polys [sizeQl][N] ->
+// 2 polys [sizeQl-1][N]
 int ref_ckks_rescale(void* hv, uint32_t sizeQl, const uint64_t* ct, uint64_t* out) {
     auto* h = static_cast<CkksCtx*>(hv);
     return guarded([&] {
         auto a = make_ct(h, sizeQl, ct, 2);
         a->SetNoiseScaleDeg(2);
-        auto c = h->cc->GetScheme()->ModReduce(a, 1);
+        auto c = h->cc->GetScheme()->ModReduceInternal(a, 1);
+        if (c->GetElements()[0].GetNumOfElements() != sizeQl - 1)
+            OPENFHE_THROW("unexpected rescale output shape");
         dump_poly(c->GetElements()[0], out);
         dump_poly(c->GetElements()[1], out + (size_t)(sizeQl - 1) * h->N);
     });

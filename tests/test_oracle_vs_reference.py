@@ -1,0 +1,117 @@
+"""Live differential test: the C restatement against the UNMODIFIED reference compiled into oracle/_ref
+(skipped where that build is absent; the committed golden vectors cover those boxes)."""
+import numpy as np
+import pytest
+
+from oracle_lib import seeded_residues
+
+
+def test_number_theory(oracle, reference):
+    o, r = oracle.L, reference.L
+    for bits, m in [(59, 1 << 17), (60, 1 << 13), (50, 1 << 13), (28, 16), (16, 16)]:
+        assert o.orc_first_prime(bits, m) == r.ref_first_prime(bits, m)
+        q = o.orc_last_prime(bits, m)
+        assert q == r.ref_last_prime(bits, m)
+        assert o.orc_previous_prime(q, m) == r.ref_previous_prime(q, m)
+        assert o.orc_next_prime(q, m) == r.ref_next_prime(q, m)
+        assert o.orc_root_of_unity(m, q) == r.ref_root_of_unity(m, q)
+
+
+def test_scalar_modmul(oracle, reference):
+    o, r = oracle.L, reference.L
+    rng = np.random.default_rng(11)
+    for q in (113, 268435361, 1152921504606830593, 576460752303415297):
+        mu = o.orc_barrett_mu(q)
+        for _ in range(300):
+            a, b = int(rng.integers(0, q)), int(rng.integers(0, q))
+            assert o.orc_mulmod_barrett(a, b, q, mu) == r.ref_modmul_barrett(a, b, q)
+            assert o.orc_shoup_precon(b, q) == r.ref_prep_modmul_const(b, q)
+            assert o.orc_mulmod_shoup(a, b, o.orc_shoup_precon(b, q), q) == r.ref_modmul_const(a, b, q)
+            hi, lo = int(rng.integers(0, 1 << 62)), int(rng.integers(0, 1 << 63))
+            assert oracle.barrett128(hi, lo, q) == r.ref_barrett128(hi, lo, q)
+
+
+@pytest.mark.parametrize("logN", [1, 3, 6, 10, 12, 13])
+def test_ntt(oracle, reference, logN):
+    N = 1 << logN
+    q = oracle.L.orc_last_prime(60 if logN > 4 else 28, 2 * N)
+    root = oracle.L.orc_root_of_unity(2 * N, q)
+    for seed, x in enumerate([seeded_residues(3, [q], N)[0], np.zeros(N, dtype=np.uint64),
+                              np.full(N, q - 1, dtype=np.uint64), np.full(N, 12345 % q, dtype=np.uint64)]):
+        y = oracle.ntt_fwd(q, root, x)
+        assert (y == reference.ntt_fwd(q, root, x)).all()
+        assert (oracle.ntt_inv(q, root, y) == reference.ntt_inv(q, root, y)).all()
+    to, tr = oracle.twiddles(q, root, N), reference.twiddles(q, root, N)
+    for a, b in zip(to[:4], tr[:4]):
+        assert (a == b).all()
+    assert to[4:] == tr[4:]
+
+
+def test_limb_ops(oracle, reference):
+    N = 256
+    q0 = oracle.L.orc_last_prime(60, 2 * N)
+    q = np.array([q0, oracle.L.orc_previous_prime(q0, 2 * N), oracle.L.orc_last_prime(45, 2 * N)], dtype=np.uint64)
+    roots = np.array([oracle.L.orc_root_of_unity(2 * N, int(x)) for x in q], dtype=np.uint64)
+    a, b = seeded_residues(1, q, N), seeded_residues(2, q, N)
+    a[0, :4] = [0, q[0] - 1, 1, q[0] // 2]
+    b[0, :4] = [0, q[0] - 1, q[0] - 1, q[0] // 2 + 1]
+    for op in range(4):
+        assert (oracle.dcrt_binop(q, op, a, b) == reference.dcrt_binop(q, roots, op, a, b)).all()
+    s = np.array([5, int(q[1]) - 1, 123456789], dtype=np.uint64)
+    assert (oracle.dcrt_times_scalars(q, a, s) == reference.dcrt_times_scalars(q, roots, a, s)).all()
+    for k in (3, 5, 25, 2 * N - 1):
+        assert (oracle.automorphism_map(N, k) == reference.automorphism_map(N, k)).all()
+        assert (oracle.dcrt_automorphism(k, a) == reference.dcrt_automorphism(q, roots, k, a)).all()
+    for f, t in [(0, 1), (1, 0), (0, 2), (2, 0)]:
+        assert (oracle.switch_modulus(q[f], q[t], a[f]) == reference.switch_modulus(q[f], q[t], a[f])).all()
+
+
+@pytest.mark.parametrize("args", [(1 << 10, 5, 50, 60, 0, 0), (1 << 11, 7, 40, 50, 2, 1), (1 << 10, 6, 59, 60, 3, 2),
+                                  (1 << 9, 1, 45, 50, 0, 0)])
+def test_ckks_tables_and_keyswitch(oracle, reference, args):
+    N = args[0]
+    oc, rc = oracle.ckks(*args), reference.ckks(*args)
+    try:
+        assert (oc.N, oc.sizeQ, oc.sizeP, oc.dnum, oc.alpha) == (rc.N, rc.sizeQ, rc.sizeP, rc.dnum, rc.alpha)
+        assert (oc.moduli == rc.moduli).all() and (oc.roots == rc.roots).all()
+        for f in ("PInvModq", "PModq", "PHatInvModp", "PHatModq"):
+            assert (getattr(oc, f)() == getattr(rc, f)()).all(), f
+        for sizeQl in range(1, oc.sizeQ + 1):
+            for part in range(oc.num_digits(sizeQl)):
+                ds = oc.digit_size(sizeQl, part)
+                assert (oc.PartQlHatInvModq(part, ds) == rc.PartQlHatInvModq(part, ds)).all()
+                a1, b1 = oc.PartQlHatModp(sizeQl, part)
+                a2, b2 = rc.PartQlHatModp(sizeQl, part)
+                assert (a1 == a2).all() and (b1 == b2).all()
+            if sizeQl > 1:
+                x1, x2 = oc.rescale_tables(sizeQl), rc.rescale_tables(sizeQl)
+                assert (x1[0] == x2[0]).all() and (x1[1] == x2[1]).all()
+        ea, eb = rc.evalmult_key()
+        for sizeQl in sorted({oc.sizeQ, max(1, oc.sizeQ - 1), min(2, oc.sizeQ), 1}, reverse=True):
+            c = seeded_residues(7 + sizeQl, oc.moduli[:sizeQl], N)
+            assert (oc.modup(sizeQl, c) == rc.modup(sizeQl, c)).all()
+            # a10 alone, on the coefficient-format digit, and a11 alone
+            ds = oc.digit_size(sizeQl, 0)
+            hatinv = oc.PartQlHatInvModq(0, ds)
+            hatmod, compl = oc.PartQlHatModp(sizeQl, 0)
+            conv = oracle.approx_switch_crt_basis(oc.moduli[:ds], hatinv, compl, hatmod, c[:ds])
+            assert (conv == rc.approx_switch_crt_basis_digit(sizeQl, 0, c[:ds])).all()
+            e = seeded_residues(70 + sizeQl, oc.moduli_QlP(sizeQl), N)
+            assert (oc.approx_mod_down(sizeQl, e) == rc.approx_mod_down(sizeQl, e)).all()
+            k1, k2 = oc.keyswitch_core(sizeQl, c, ea, eb), rc.keyswitch_core(sizeQl, c)
+            assert (k1[0] == k2[0]).all() and (k1[1] == k2[1]).all()
+            ct1 = np.stack([seeded_residues(11, oc.moduli[:sizeQl], N), seeded_residues(12, oc.moduli[:sizeQl], N)])
+            ct2 = np.stack([seeded_residues(13, oc.moduli[:sizeQl], N), seeded_residues(14, oc.moduli[:sizeQl], N)])
+            assert (oc.evalmult(sizeQl, ct1, ct2, ea, eb) == rc.evalmult(sizeQl, ct1, ct2)).all()
+            if sizeQl > 1:
+                assert (oc.rescale_poly(sizeQl, c) == rc.rescale_poly(sizeQl, c)).all()
+                r2 = rc.rescale(sizeQl, ct1)
+                assert (oc.rescale_poly(sizeQl, ct1[0]) == r2[0]).all()
+        for index in (1, -2):
+            k, ra, rb = rc.rotate_key(index)
+            sizeQl = oc.sizeQ
+            ct = np.stack([seeded_residues(21, oc.moduli[:sizeQl], N), seeded_residues(22, oc.moduli[:sizeQl], N)])
+            assert (oc.automorphism_ct(sizeQl, k, ct, ra, rb) == rc.rotate(sizeQl, index, ct)).all()
+    finally:
+        oc.close()
+        rc.close()
