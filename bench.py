@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- CKKS EvalMult + relinearisation throughput (BASELINE.json metric) on N B200s, next to the reference CPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one homomorphic multiplication (EvalMultCore tensor + HYBRID key switch of c2 + the two adds) of two
+synthetic full-level ciphertexts at BASELINE.json configs[1]: N = 2^16, depth 44 (45 Q + 15 P limbs), scaleModSize 59,
+firstModSize 60, HYBRID with dnum 3.  Prints ONE JSON line (rank 0).
+
+  value        device-resident throughput (inputs already in HBM), mults/s summed over all ranks, CUDA-event timed,
+               max over ranks
+  e2e          the same operation through the host-buffer C-ABI call (pinned host memory -> device -> host)
+  roofline     the dominant kernel family (the limb NTT: strided + tile kernel pair) timed alone on a slab larger
+               than L2: algorithmic bytes 16*N per limb-NTT / CUDA-event time vs the measured HBM peak
+  cpu_baseline the unmodified reference (oracle/_ref) -- or the C oracle port if that build is absent -- timed on
+               this box's host cores on a bounded sample of the same workload
+Multi-GPU (round 1): independent ciphertext pairs per rank (replicas, no collective on the data path) -> "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "openfhe-development_b200"))
+
+CFG = dict(N=1 << 16, depth=44, scale_bits=59, first_bits=60, dnum=0, scal_tech=0)
+WORKLOAD = "CKKS EvalMult+relinearize, N=2^16, depth 44 (45 Q + 15 P limbs), scaleMod 59, firstMod 60, HYBRID dnum 3"
+METRIC = "ckks_evalmult_relin_per_s"
+UNIT = "mults/s"
+# kernels launched by one EvalMult (hks.cu): tensor 1, INTT 2, base conversion 3, NTT 2, inner product 1,
+# ModDown: INTT 2 + base conversion 1 + NTT 2 + (x-conv)*PInv+addend 2
+LAUNCHES_PER_STEP = 16
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def cpu_reference_run(steps, warmup, threads=None):
+    """Times cc->EvalMult of the unmodified reference (oracle/_ref) on the workload, or the C oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, Reference, reference_available, seeded_residues
+
+    cores = threads or len(os.sched_getaffinity(0))
+    N = CFG["N"]
+    if reference_available():
+        ref = Reference()
+        ref.L.ref_set_threads(cores)
+        c = ref.ckks(N, CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
+        kind = "reference"
+    else:
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        c = Oracle().ckks(N, CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
+        kind = "port"
+    sizeQl = c.sizeQ
+    ct1 = np.stack([seeded_residues(1, c.moduli[:sizeQl], N), seeded_residues(2, c.moduli[:sizeQl], N)])
+    ct2 = np.stack([seeded_residues(3, c.moduli[:sizeQl], N), seeded_residues(4, c.moduli[:sizeQl], N)])
+    if kind == "reference":
+        sec = c.time_evalmult(sizeQl, ct1, ct2, warmup, steps)
+    else:
+        ea = seeded_residues(5, np.tile(c.moduli, c.dnum), N).reshape(c.dnum, c.sizeQP, N)
+        eb = seeded_residues(6, np.tile(c.moduli, c.dnum), N).reshape(c.dnum, c.sizeQP, N)
+        for _ in range(warmup):
+            c.evalmult(sizeQl, ct1, ct2, ea, eb)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            c.evalmult(sizeQl, ct1, ct2, ea, eb)
+        sec = (time.perf_counter() - t0) / steps
+    c.close()
+    return dict(value=1.0 / sec, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{steps} EvalMult calls after {warmup} warm-up on the full workload "
+                       f"({'cc->EvalMult of the unmodified reference, OpenMP' if kind == 'reference' else 'C oracle port, OpenMP'})"), sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(a.steps, 8))
+        base, sec = cpu_reference_run(steps, max(1, min(a.warmup, 2)))
+        line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=steps,
+                    warmup=max(1, min(a.warmup, 2)), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="u64", data="synthetic", config={"workload": WORKLOAD},
+                    cpu_baseline=base, e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0,
+                                                d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+
+    import ofhe_b200 as m
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    p = m.ckks_paramgen(CFG["N"], CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
+    N, sizeQ, sizeP, dnum = p["N"], p["sizeQ"], p["sizeP"], p["dnum"]
+    ctx = m.Context(local_rank)
+    ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+    hks = m.Hks(ring, sizeQ, sizeP, dnum)
+    evk = m.EvalKey(hks, seed=1234 + rank)
+    sizeQl = sizeQ
+    idx2 = list(range(sizeQl)) * 2
+    ct1, ct2, out = ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N)
+    ring.fill_uniform(ct1.view(2 * sizeQl, N), idx2, 11 + rank)
+    ring.fill_uniform(ct2.view(2 * sizeQl, N), idx2, 12 + rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----------------------------------------------------------------------------
+    for _ in range(a.warmup):
+        hks.evalmult(sizeQl, ct1, ct2, evk, out)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        hks.evalmult(sizeQl, ct1, ct2, evk, out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    t = torch.tensor([ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * a.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, copies inside the timed region) ----
+    h1 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
+    h2 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
+    ho = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
+    h1.copy_(ct1.cpu())
+    h2.copy_(ct2.cpu())
+    e2e_steps = max(3, min(a.steps, 10))
+    for _ in range(2):
+        hks.evalmult_host(sizeQl, h1, h2, evk, ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hks.evalmult_host(sizeQl, h1, h2, evk, ho)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert bool((ho.cuda() == out).all()), "host-buffer path and device path disagree"
+    ct_bytes = 2 * sizeQl * N * 8
+
+    # ---- roofline of the dominant kernel family: forward limb-NTT on a slab larger than L2 ---------------------
+    L = 240  # 240 limbs x 512 KiB = 120 MiB in + out in place; > L2 together with its 60 MiB of twiddles
+    slab = ctx.zeros(L, N)
+    lidx = [i % (sizeQ + sizeP) for i in range(L)]
+    ring.fill_uniform(slab, lidx, 99)
+    for _ in range(3):
+        ring.ntt_fwd(slab, slab, lidx)
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        ring.ntt_fwd(slab, slab, lidx)
+    e1.record()
+    torch.cuda.synchronize()
+    ntt_ms = e0.elapsed_time(e1) / reps
+    peak, peak_src = measured_peak_gbs()
+    ntt_bytes = 16.0 * N * L
+    achieved = ntt_bytes / (ntt_ms * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="ntt_fwd (ntt_fwd_strided<4> + ntt_fwd_tile)", achieved=achieved, peak=peak,
+                    unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_launch=ntt_bytes, us_per_limb_ntt=ntt_ms * 1e3 / L)
+
+    line = None
+    if rank == 0:
+        base = None
+        if not a.no_cpu_baseline:
+            base, _ = cpu_reference_run(a.cpu_steps, 1)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
+                    data="synthetic",
+                    config={"workload": WORKLOAD, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                            "l2": "per-step working set ~0.6 GB (evk 180 MiB + digits 90 MiB + ...) exceeds the 126 MB L2"},
+                    e2e=dict(value=world * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=2 * ct_bytes,
+                             d2h_bytes_per_step=ct_bytes, steps=e2e_steps),
+                    gpu_launches=LAUNCHES_PER_STEP * a.steps, roofline=roofline, cpu_baseline=base,
+                    clocks=sampler.summary())
+        print(json.dumps(line))
+    for o in (evk, hks, ring, ctx):
+        o.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
