@@ -6,96 +6,148 @@
 //     out_j = ( sum_i y_i * QHatModp[i][j] )  mod p_j               (128-bit accumulate + Barrett)
 // Results are the same canonical residues as the reference's Mul128 / BarrettUint128ModUint64 path.
 //
-// GPU formulation: one thread per coefficient, all source residues premultiplied into registers, the
-// conversion matrix broadcast from shared memory.  The 60x60-bit multiply-accumulate is done on 30-bit
-// halves so that each MAC is exactly four IMAD.WIDE.U32 with NO carry chain:
+// GPU formulation.  grid = (coefficient blocks, output groups, batch): a thread owns two coefficients and JPT = 8
+// target limbs (a 15 -> 45 conversion of 65536 coefficients runs on 6 x 32768 threads), and every 128-bit shared-memory
+// read of the conversion matrix feeds 16 IMADs.  The source
+// residues arrive already multiplied by QHatInvModq when the caller folded that constant into the last stage of the
+// inverse NTT (`premultiplied`), else the kernel does the Shoup multiply itself.  The 60x60-bit
+// multiply-accumulate works on 30-bit halves so that each MAC is exactly four IMAD.WIDE.U32 with NO carry chain
+// (the integer-FMA pipe issues at full rate on sm_100, the ALU pipe carrying IADD3 at half rate):
 //     y = y1*2^30 + y0,  m = m1*2^30 + m0   ->   c0 += y0*m0; c1a += y0*m1; c1b += y1*m0; c2 += y1*m1
-// Each partial sum stays below 2^64 for up to 16 terms; every 16 source limbs the four sums are folded into
-// a 128-bit accumulator.  Requires q_i, p_j < 2^60 (MAX_MODULUS_SIZE, core/include/math/hal/basicint.h:48).
+// Each partial sum stays below 2^64 for 16 terms.  The four column sums are then reduced WITHOUT assembling a
+// 128-bit value: S = c0 + (c1a + c1b) 2^30 + c2 2^60 (mod p) is formed from Shoup-lazy products with the constants
+// 2^30 mod p and 2^60 mod p (IMAD work again, instead of the shift / carry chains of a 128-bit Barrett reduction that
+// would make the half-rate ALU pipe the bottleneck).  The matrix slice of the CTA's output group is zero-padded in shared memory to 16*CH x JPT, so the
+// MAC loops have compile-time bounds and no predication.  Requires q_i, p_j < 2^60 (MAX_MODULUS_SIZE,
+// core/include/math/hal/basicint.h:48).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace ofhe {
 namespace {
 
 constexpr uint32_t kMask30 = (1u << 30) - 1;
+constexpr int kJPT         = 8;    // target limbs per thread
+constexpr int kThreads     = 128;  // coefficients per CTA
 
 struct BConvDev {
     uint32_t sizeQ, sizeP;
-    const uint64_t* qhatinv;  // [sizeQ][2]
+    const uint64_t* qhatinv;  // [sizeQ][2]  (w, Shoup(w))
     const uint2* mat;         // [sizeQ][sizeP]  (lo30, hi30)
 };
 
-template <int MAXQ>
-__global__ void __launch_bounds__(128) bconv_kernel(RingDev r, BConvDev t, LimbMap qmap, LimbMap pmap,
-                                                     const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
-                                                     size_t in_stride, size_t out_stride) {
-    in += blockIdx.y * in_stride;
-    out += blockIdx.y * out_stride;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: mat[sizeQ*sizeP] (uint2) | src consts [sizeQ][3] (q, w, ws) | dst consts [sizeP][3] (p, mu_hi, mu_lo)
-    uint2* s_mat    = reinterpret_cast<uint2*>(smem_raw);
-    uint64_t* s_src = reinterpret_cast<uint64_t*>(s_mat + (size_t)t.sizeQ * t.sizeP);
-    uint64_t* s_dst = s_src + 3 * t.sizeQ;
-    for (uint32_t i = threadIdx.x; i < t.sizeQ * t.sizeP; i += blockDim.x)
-        s_mat[i] = t.mat[i];
-    for (uint32_t i = threadIdx.x; i < t.sizeQ; i += blockDim.x) {
-        s_src[3 * i]     = r.mc[qmap.idx[i]].q;
-        s_src[3 * i + 1] = t.qhatinv[2 * i];
-        s_src[3 * i + 2] = t.qhatinv[2 * i + 1];
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
+
+// CH chunks of 16 source limbs; kCPT coefficients per thread (2 when the register budget allows: every 128-bit
+// matrix read from shared memory then feeds 16 IMADs)
+template <int CH, int kCPT>
+__global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, LimbMap qmap, LimbMap pmap,
+                                                          const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                          size_t in_stride, size_t out_stride, int premultiplied) {
+    constexpr int MAXQ = 16 * CH;
+    __shared__ __align__(16) uint2 s_mat[MAXQ * kJPT];
+    __shared__ uint64_t s_src[MAXQ * 3];  // q, w, ws
+    __shared__ uint64_t s_dst[kJPT * 6];  // p, 2^30 mod p (+Shoup), 2^60 mod p (+Shoup), floor(2^64/p)
+    in += blockIdx.z * in_stride;
+    out += blockIdx.z * out_stride;
+    const uint32_t j0 = blockIdx.y * kJPT;
+    for (uint32_t e = threadIdx.x; e < MAXQ * kJPT; e += kThreads) {
+        const uint32_t i = e / kJPT, j = j0 + e % kJPT;
+        s_mat[e] = (i < t.sizeQ && j < t.sizeP) ? t.mat[(size_t)i * t.sizeP + j] : make_uint2(0u, 0u);
     }
-    for (uint32_t j = threadIdx.x; j < t.sizeP; j += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < MAXQ; i += kThreads) {
+        const bool ok    = i < t.sizeQ;
+        s_src[3 * i]     = ok ? r.mc[qmap.idx[i]].q : 1;
+        s_src[3 * i + 1] = ok ? t.qhatinv[2 * i] : 0;
+        s_src[3 * i + 2] = ok ? t.qhatinv[2 * i + 1] : 0;
+    }
+    if (threadIdx.x < kJPT) {
+        const uint32_t j   = j0 + threadIdx.x < t.sizeP ? j0 + threadIdx.x : t.sizeP - 1;
         const ModConst& mc = r.mc[pmap.idx[j]];
-        s_dst[3 * j]       = mc.q;
-        s_dst[3 * j + 1]   = mc.mu128_hi;
-        s_dst[3 * j + 2]   = mc.mu128_lo;
+        uint64_t* d        = s_dst + 6 * threadIdx.x;
+        d[0] = mc.q, d[1] = mc.r30, d[2] = mc.r30s, d[3] = mc.r60, d[4] = mc.r60s, d[5] = mc.one_s;
     }
     __syncthreads();
 
-    const uint32_t N  = r.N;
-    const uint32_t rr = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rr >= N)
-        return;
-    uint32_t y0[MAXQ], y1[MAXQ];
+    const uint32_t N   = r.N;
+    const uint32_t rr0 = blockIdx.x * (kThreads * kCPT) + threadIdx.x;  // coefficient c of this thread: rr0 + c*kThreads
+    uint32_t y0[kCPT][MAXQ], y1[kCPT][MAXQ];
 #pragma unroll
-    for (int i = 0; i < MAXQ; ++i) {
-        if (i < (int)t.sizeQ) {
-            uint64_t x = in[(size_t)qmap.pos[i] * N + rr];
-            uint64_t y = shoup(x, s_src[3 * i + 1], s_src[3 * i + 2], s_src[3 * i]);
-            y0[i]      = (uint32_t)y & kMask30;
-            y1[i]      = (uint32_t)(y >> 30);
-        }
-        else {
-            y0[i] = 0;
-            y1[i] = 0;
+    for (int c = 0; c < kCPT; ++c) {
+        const uint32_t rr = min(rr0 + c * kThreads, N - 1);  // clamped (branch-free); stores are predicated below
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i) {
+            const int ii = i < (int)t.sizeQ ? i : 0;  // padded rows re-read row 0 and are zeroed
+            uint64_t y   = in[(size_t)qmap.pos[ii] * N + rr];
+            if (!premultiplied)
+                y = shoup(y, s_src[3 * ii + 1], s_src[3 * ii + 2], s_src[3 * ii]);
+            y        = i < (int)t.sizeQ ? y : 0;
+            y0[c][i] = (uint32_t)y & kMask30;
+            y1[c][i] = (uint32_t)(y >> 30);
         }
     }
-    for (uint32_t j = 0; j < t.sizeP; ++j) {
-        uint64_t hi = 0, lo = 0;
+    // the output-pair loop stays rolled: the fully unrolled body (64 KB of code) thrashed the instruction cache
+#pragma unroll 1
+    for (int j = 0; j < kJPT; j += 2) {
+        uint64_t total[kCPT][2];
 #pragma unroll
-        for (int c = 0; c < MAXQ; c += 16) {
-            if (c < (int)t.sizeQ) {
-                uint64_t c0 = 0, c1a = 0, c1b = 0, c2 = 0;
+        for (int c = 0; c < kCPT; ++c)
+            total[c][0] = total[c][1] = 0;
 #pragma unroll
-                for (int i = c; i < c + 16 && i < MAXQ; ++i) {
-                    if (i < (int)t.sizeQ) {
-                        uint2 m = s_mat[(size_t)i * t.sizeP + j];
-                        c0 += (uint64_t)y0[i] * m.x;
-                        c1a += (uint64_t)y0[i] * m.y;
-                        c1b += (uint64_t)y1[i] * m.x;
-                        c2 += (uint64_t)y1[i] * m.y;
-                    }
+        for (int ch = 0; ch < CH; ++ch) {
+            uint64_t a[kCPT][2][4];  // [coefficient][output j, j+1][c0, c1a, c1b, c2]
+#pragma unroll
+            for (int c = 0; c < kCPT; ++c)
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+                    a[c][o][0] = a[c][o][1] = a[c][o][2] = a[c][o][3] = 0;
+#pragma unroll
+            for (int i = 16 * ch; i < 16 * ch + 16; ++i) {
+                const uint4 m = *reinterpret_cast<const uint4*>(&s_mat[i * kJPT + j]);  // (lo,hi) of j and of j+1
+#pragma unroll
+                for (int c = 0; c < kCPT; ++c) {
+                    a[c][0][0] = mad_wide(y0[c][i], m.x, a[c][0][0]);
+                    a[c][0][1] = mad_wide(y0[c][i], m.y, a[c][0][1]);
+                    a[c][0][2] = mad_wide(y1[c][i], m.x, a[c][0][2]);
+                    a[c][0][3] = mad_wide(y1[c][i], m.y, a[c][0][3]);
+                    a[c][1][0] = mad_wide(y0[c][i], m.z, a[c][1][0]);
+                    a[c][1][1] = mad_wide(y0[c][i], m.w, a[c][1][1]);
+                    a[c][1][2] = mad_wide(y1[c][i], m.z, a[c][1][2]);
+                    a[c][1][3] = mad_wide(y1[c][i], m.w, a[c][1][3]);
                 }
-                // fold: S += c0 + (c1a + c1b) * 2^30 + c2 * 2^60
-                unsigned __int128 s = ((unsigned __int128)hi << 64) | lo;
-                s += c0;
-                s += (unsigned __int128)c1a << 30;
-                s += (unsigned __int128)c1b << 30;
-                s += (unsigned __int128)c2 << 60;
-                hi = (uint64_t)(s >> 64);
-                lo = (uint64_t)s;
+            }
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const uint64_t* d = s_dst + 6 * (j + o);
+                const uint64_t np = 0 - d[0];
+#pragma unroll
+                for (int c = 0; c < kCPT; ++c) {
+                    // v = c0 + (c1a + c1b) 2^30 + c2 2^60 (mod p), below 8p: the four Shoup-lazy terms
+                    // c_k w_k - floor(c_k w_k' / 2^64) p share ONE multiplication by -p (everything is mod 2^64 and
+                    // the true value is below 2^63, so the wrapped sum is exact)
+                    const uint64_t* a4 = a[c][o];
+                    const uint64_t h   = mulhi(a4[0], d[5]) + mulhi(a4[1], d[2]) + mulhi(a4[2], d[2]) + mulhi(a4[3], d[4]);
+                    const uint64_t v   = a4[0] + (a4[1] + a4[2]) * d[1] + a4[3] * d[3] + h * np;
+                    total[c][o] += CH == 1 ? v : lazy_reduce_n(v, d[5], np);  // CH <= 4 chunks: < 8p
+                }
             }
         }
-        out[(size_t)pmap.pos[j] * N + rr] = barrett128(hi, lo, s_dst[3 * j], s_dst[3 * j + 1], s_dst[3 * j + 2]);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const uint64_t* d = s_dst + 6 * (j + o);
+#pragma unroll
+            for (int c = 0; c < kCPT; ++c) {
+                const uint32_t rr = rr0 + c * kThreads;
+                if (j0 + j + o < t.sizeP && rr < N)
+                    out[(size_t)pmap.pos[j0 + j + o] * N + rr] = csub(lazy_reduce_n(total[c][o], d[5], 0 - d[0]), d[0]);
+            }
+        }
     }
 }
 
@@ -109,29 +161,28 @@ BConv::~BConv() {
 }
 
 void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* out, uint32_t batch, size_t in_stride,
-                  size_t out_stride, cudaStream_t st) {
-    if (t.sizeP == 0 || t.sizeQ == 0)
+                  size_t out_stride, bool premultiplied, cudaStream_t st) {
+    if (t.sizeP == 0 || t.sizeQ == 0 || batch == 0)
         return;
-    BConvDev d{t.sizeQ, t.sizeP, t.qhatinv_d, reinterpret_cast<const uint2*>(t.mat_d)};
-    size_t smem = (size_t)t.sizeQ * t.sizeP * sizeof(uint2) + 3 * sizeof(uint64_t) * (t.sizeQ + t.sizeP);
-    const int threads = 128;
-    dim3 grid((r.N + threads - 1) / threads, batch);
     OFHE_REQUIRE(t.sizeQ <= 64, "base conversion supports at most 64 source limbs");
-    if (t.sizeQ <= 16) {
-        if (smem > 48 * 1024)
-            OFHE_CUDA(cudaFuncSetAttribute(bconv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bconv_kernel<16><<<grid, threads, smem, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride);
-    }
-    else if (t.sizeQ <= 32) {
-        if (smem > 48 * 1024)
-            OFHE_CUDA(cudaFuncSetAttribute(bconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bconv_kernel<32><<<grid, threads, smem, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride);
-    }
-    else {
-        if (smem > 48 * 1024)
-            OFHE_CUDA(cudaFuncSetAttribute(bconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bconv_kernel<64><<<grid, threads, smem, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride);
-    }
+    BConvDev d{t.sizeQ, t.sizeP, t.qhatinv_d, reinterpret_cast<const uint2*>(t.mat_d)};
+    static const int cpt1 = [] {
+        const char* e = getenv("OFHE_BCONV_CPT");  // tuning knob: coefficients per thread for <= 16 source limbs
+        return e ? atoi(e) : 1;
+    }();
+    const int cpt = t.sizeQ <= 16 ? (cpt1 == 1 ? 1 : 2) : 1;
+    dim3 grid((r.N + kThreads * cpt - 1) / (kThreads * cpt), (t.sizeP + kJPT - 1) / kJPT, batch);
+    const int pm = premultiplied ? 1 : 0;
+    if (t.sizeQ <= 16 && cpt == 2)
+        bconv_kernel<1, 2><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+    else if (t.sizeQ <= 16)
+        bconv_kernel<1, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+    else if (t.sizeQ <= 32)
+        bconv_kernel<2, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+    else if (t.sizeQ <= 48)
+        bconv_kernel<3, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+    else
+        bconv_kernel<4, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
     OFHE_CUDA(cudaGetLastError());
 }
 

@@ -257,7 +257,7 @@ int ofhe_approx_switch_crt_basis(ofhe_ring* ring, uint32_t n_src, const uint32_t
                 it = ring->bconv_cache.emplace(key, build_bconv(*ring->r, n_src, src_idx_h, n_dst, dst_idx_h)).first;
             t = it->second.get();
         }
-        launch_bconv(*ring->r, *t, in_d, out_d, 1, 0, 0, S(stream));
+        launch_bconv(*ring->r, *t, in_d, out_d, 1, 0, 0, /*premultiplied=*/false, S(stream));
     });
 }
 

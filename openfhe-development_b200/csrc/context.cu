@@ -91,6 +91,11 @@ Ring* ring_create(Context* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* m
         hm::u128 mu128 = ~(hm::u128)0 / q;  // == floor(2^128 / q) for q not a power of two
         mc.mu128_hi  = (uint64_t)(mu128 >> 64);
         mc.mu128_lo  = (uint64_t)mu128;
+        mc.r30       = (uint64_t(1) << 30) % q;
+        mc.r30s      = hm::shoup_const(mc.r30, q);
+        mc.r60       = (uint64_t(1) << 60) % q;
+        mc.r60s      = hm::shoup_const(mc.r60, q);
+        mc.one_s     = hm::shoup_const(1 % q, q);
         mc.nInv      = hm::inv(N % q, q);
         mc.nInvS     = hm::shoup_const(mc.nInv, q);
         mc.w1nInv    = hm::mul(v[1].w, mc.nInv, q);
@@ -109,6 +114,14 @@ Ring* ring_create(Context* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* m
         throw;
     }
     return r;
+}
+
+void make_inv_fold(const Ring& r, uint32_t mi, uint64_t s, uint64_t out4[4]) {
+    const ModConst& mc = r.mc_h[mi];
+    out4[0] = hm::mul(mc.nInv, s % mc.q, mc.q);
+    out4[1] = hm::shoup_const(out4[0], mc.q);
+    out4[2] = hm::mul(mc.w1nInv, s % mc.q, mc.q);
+    out4[3] = hm::shoup_const(out4[2], mc.q);
 }
 
 Context* context_create(int device) {

@@ -89,6 +89,12 @@ Hks::Hks(Ring* r, uint32_t sizeQ_, uint32_t sizeP_, uint32_t dnum_) : ring(r), s
     }
 }
 Hks::~Hks() = default;
+Hks::Level::~Level() {
+    if (fold_modup_d)
+        cudaFree(fold_modup_d);
+    if (fold_moddown_d)
+        cudaFree(fold_moddown_d);
+}
 
 Hks::Level& Hks::level(uint32_t sizeQl) {
     OFHE_REQUIRE(sizeQl >= 1 && sizeQl <= sizeQ, "hks: level out of range");
@@ -127,6 +133,30 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
                 lv->map_modup_ntt.pos[n] = (uint16_t)(j * sizeQlP + i);
             }
         lv->modup.push_back(make_bconv(r, si, sp, di, dp));
+    }
+    {   // QHatInv of every source limb folded into the constants of the inverse NTT that precedes the conversion
+        std::vector<uint64_t> fold(4 * (size_t)sizeQl);
+        for (uint32_t j = 0; j < lv->n_digits; ++j) {
+            const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
+            for (uint32_t i = 0; i < ds; ++i) {
+                uint64_t q = r.moduli[s + i];
+                uint64_t w = hm::inv(hm::prod_mod(r.moduli.data() + s, ds, (long)i, q), q);
+                make_inv_fold(r, s + i, w, &fold[4 * (size_t)(s + i)]);
+            }
+        }
+        OFHE_CUDA(cudaMalloc(&lv->fold_modup_d, sizeof(uint64_t) * fold.size()));
+        OFHE_CUDA(cudaMemcpy(lv->fold_modup_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
+    }
+    if (sizeP) {
+        const uint64_t* P = r.moduli.data() + sizeQ;
+        std::vector<uint64_t> fold(8 * (size_t)sizeP);
+        for (uint32_t b = 0; b < 2; ++b)
+            for (uint32_t j = 0; j < sizeP; ++j) {
+                uint64_t w = hm::inv(hm::prod_mod(P, sizeP, (long)j, P[j]), P[j]);
+                make_inv_fold(r, sizeQ + j, w, &fold[4 * (size_t)(b * sizeP + j)]);
+            }
+        OFHE_CUDA(cudaMalloc(&lv->fold_moddown_d, sizeof(uint64_t) * fold.size()));
+        OFHE_CUDA(cudaMemcpy(lv->fold_moddown_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
     }
     // ---- ModDown: P rows -> Ql rows  (PHatInvModp / PHatModq, rns-cryptoparameters.cpp:214-229)
     if (sizeP) {
@@ -183,12 +213,12 @@ void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* 
     const Ring& r  = *ring;
     const size_t N = r.N, sizeQlP = sizeQl + sizeP;
     // 1. all digits at once: coefficient-format copy of c                            (keyswitch-hybrid.cpp:359)
-    launch_ntt_inv(r, c, coeff_tmp, lv.map_Ql, st);
+    launch_ntt_inv(r, c, coeff_tmp, lv.map_Ql, st, nullptr, lv.fold_modup_d);  // y_i = INTT(c)_i * QHatInv_i
     for (uint32_t j = 0; j < lv.n_digits; ++j) {
         uint64_t* D      = digits + (size_t)j * sizeQlP * N;
         const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
         // 2. fast base conversion straight into the complementary rows of D_j           (:360-365)
-        launch_bconv(r, *lv.modup[j], coeff_tmp, D, 1, 0, 0, st);
+        launch_bconv(r, *lv.modup[j], coeff_tmp, D, 1, 0, 0, /*premultiplied=*/true, st);
         // 3. the digit's own rows keep the ORIGINAL evaluation-format limbs of c          (:372-373)
         OFHE_CUDA(cudaMemcpyAsync(D + (size_t)s * N, c + (size_t)s * N, sizeof(uint64_t) * ds * N,
                                   cudaMemcpyDeviceToDevice, st));
@@ -218,9 +248,9 @@ void Hks::mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const
     PosMap gather;
     for (uint32_t n = 0; n < lv.map_P2.n; ++n)
         gather.pos[n] = (uint16_t)n;
-    launch_ntt_inv(r, e01, p_tmp, lv.map_P2, st, &gather);
+    launch_ntt_inv(r, e01, p_tmp, lv.map_P2, st, &gather, lv.fold_moddown_d);  // times PHatInvModp
     // P -> Ql conversion of both polynomials in one launch                                     (:987-988)
-    launch_bconv(r, *lv.moddown, p_tmp, conv_tmp, 2, (size_t)sizeP * N, (size_t)sizeQl * N, st);
+    launch_bconv(r, *lv.moddown, p_tmp, conv_tmp, 2, (size_t)sizeP * N, (size_t)sizeQl * N, /*premultiplied=*/true, st);
     // back to EVALUATION                                                                         (:1001)
     launch_ntt_fwd(r, conv_tmp, conv_tmp, lv.map_Ql2, st);
     // out = (e - conv) * P^-1 (+ addend)                                                          (:1002)

@@ -33,6 +33,9 @@ struct Hks {
         LimbMap map_P2, map_Ql2;
         std::vector<std::unique_ptr<BConv>> modup;
         std::unique_ptr<BConv> moddown;
+        uint64_t* fold_modup_d = nullptr;    // [sizeQl][4]: INTT constants with PartQlHatInvModq folded in
+        uint64_t* fold_moddown_d = nullptr;  // [2*sizeP][4]: INTT constants with PHatInvModp folded in
+        ~Level();
         ScalarVec pinv2;
         ScalarVec rescaleA, rescaleB;
     };

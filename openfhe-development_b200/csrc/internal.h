@@ -97,8 +97,12 @@ inline LimbMap make_map(const uint32_t* idx, uint32_t n) {
 // If out_pos is given, limb l is read from in + lm.pos[l] * N and written to out + out_pos->pos[l] * N.
 void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
                     const PosMap* out_pos = nullptr);
+// `fold` (device, [lm.n][4]): per-limb replacement for (nInv, Shoup, Tinv[1]*nInv, Shoup) with an extra scalar
+// folded in, see make_inv_fold(); nullptr = plain inverse transform.
 void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
-                    const PosMap* out_pos = nullptr);
+                    const PosMap* out_pos = nullptr, const uint64_t* fold = nullptr);
+// host helper: the four folded constants of limb `mod_idx` for extra scalar s
+void make_inv_fold(const Ring& r, uint32_t mod_idx, uint64_t s, uint64_t out4[4]);
 
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2, EW_NEG = 3, EW_MAC = 4 /* dst += a*b */ };
 void launch_ew(const Ring& r, EwOp op, uint64_t* dst, const uint64_t* a, const uint64_t* b, const LimbMap& lm,
@@ -135,8 +139,9 @@ struct BConv {
     ~BConv();
 };
 // `batch` independent polynomials, `in_stride` / `out_stride` words apart
+// premultiplied: the source residues already carry the factor QHatInvModq (folded into the preceding inverse NTT)
 void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* out, uint32_t batch, size_t in_stride,
-                  size_t out_stride, cudaStream_t st);
+                  size_t out_stride, bool premultiplied, cudaStream_t st);
 
 // hybrid key-switch inner product (a17)
 void launch_ks_inner_product(const Ring& r, uint32_t n_digits, const uint64_t* digits, size_t digit_stride,

@@ -22,6 +22,11 @@ struct ModConst {
     uint64_t nInvS;
     uint64_t w1nInv;    // Tinv[1] * N^-1 mod q and its Shoup constant (transformnat-impl.h:538-539)
     uint64_t w1nInvS;
+    uint64_t r30;       // 2^30 mod q, 2^60 mod q with Shoup constants, and floor(2^64 / q) (the Shoup constant of 1):
+    uint64_t r30s;      // column-wise lazy reduction of the base-conversion accumulators (baseconv.cu)
+    uint64_t r60;
+    uint64_t r60s;
+    uint64_t one_s;
     uint32_t k;         // bit length of q
     uint32_t pad;
 };
@@ -39,10 +44,21 @@ __device__ __forceinline__ uint64_t mulhi(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t shoup_lazy(uint64_t x, uint64_t w, uint64_t ws, uint64_t q) {
     return x * w - mulhi(x, ws) * q;
 }
+// same with the negated modulus nq = 2^64 - q: one multiply-add chain, no 64-bit negate on the (half-rate) ALU pipe
+__device__ __forceinline__ uint64_t shoup_lazy_n(uint64_t x, uint64_t w, uint64_t ws, uint64_t nq) {
+    return x * w + mulhi(x, ws) * nq;
+}
+__device__ __forceinline__ uint64_t lazy_reduce_n(uint64_t x, uint64_t one_s, uint64_t nq) {
+    return x + mulhi(x, one_s) * nq;
+}
 // canonical variant, identical result to NativeIntegerT::ModMulFastConst
 __device__ __forceinline__ uint64_t shoup(uint64_t x, uint64_t w, uint64_t ws, uint64_t q) {
     uint64_t r = shoup_lazy(x, w, ws, q);
     return r >= q ? r - q : r;
+}
+// x mod q into [0, 2q) for ANY 64-bit x: Shoup multiplication by 1 (one_s = floor(2^64 / q))
+__device__ __forceinline__ uint64_t lazy_reduce(uint64_t x, uint64_t one_s, uint64_t q) {
+    return x - mulhi(x, one_s) * q;
 }
 __device__ __forceinline__ uint64_t csub(uint64_t x, uint64_t q) {  // x in [0,2q) -> [0,q)
     return x >= q ? x - q : x;

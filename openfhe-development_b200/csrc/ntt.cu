@@ -26,19 +26,30 @@ __device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
     return Twiddle{v.x, v.y};
 }
 
+// Lazy-range discipline (Harvey).  On sm_100 the integer multiplier (IMAD.WIDE: 4 issue cycles per warp on the
+// fmaheavy pipe, 2 for a 32-bit IMAD) is the bottleneck of a 60-bit butterfly: a Shoup product costs 6 IMAD.WIDE +
+// 4 IMAD = 32 cycles, while the ALU pipe (IADD3 / ISETP / SEL, 2 cycles each) has ~16 instruction slots to spare in
+// that time.  So range control is done with conditional subtractions on the ALU pipe (not with multiply-based
+// reductions), one per butterfly:  forward values live in [0,4q), inverse values in [0,2q).
+struct Mod {
+    uint64_t q, nq, twoq, one_s;  // nq = 2^64 - q
+};
+__device__ __forceinline__ Mod make_mod(const ModConst& mc) {
+    return Mod{mc.q, 0 - mc.q, 2 * mc.q, mc.one_s};
+}
 // Cooley-Tukey butterfly, inputs/outputs in [0,4q)
-__device__ __forceinline__ void ct_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, uint64_t q, uint64_t twoq) {
-    uint64_t x = X >= twoq ? X - twoq : X;
-    uint64_t v = shoup_lazy(Y, t.w, t.ws, q);
-    X          = x + v;
-    Y          = x - v + twoq;
+__device__ __forceinline__ void ct_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, const Mod& m) {
+    const uint64_t x = X >= m.twoq ? X - m.twoq : X;        // [0,2q)
+    const uint64_t v = shoup_lazy_n(Y, t.w, t.ws, m.nq);   // [0,2q)
+    X                = x + v;
+    Y                = x - v + m.twoq;
 }
 // Gentleman-Sande butterfly, inputs/outputs in [0,2q)
-__device__ __forceinline__ void gs_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, uint64_t q, uint64_t twoq) {
-    uint64_t s = X + Y;
-    uint64_t d = X - Y + twoq;
-    X          = s >= twoq ? s - twoq : s;
-    Y          = shoup_lazy(d, t.w, t.ws, q);
+__device__ __forceinline__ void gs_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, const Mod& m) {
+    const uint64_t s = X + Y;
+    const uint64_t d = X - Y + m.twoq;
+    X                = s >= m.twoq ? s - m.twoq : s;
+    Y                = shoup_lazy_n(d, t.w, t.ws, m.nq);
 }
 
 // One stage (local depth D of R) on 2^R register-resident points; all indices are compile-time constants so the
@@ -46,69 +57,78 @@ __device__ __forceinline__ void gs_bfly(uint64_t& X, uint64_t& Y, const Twiddle&
 // tw_base = 2^s0 + u (s0 = the round's first global stage, u = the s0 index bits above this group).
 template <int R, int D>
 __device__ __forceinline__ void ct_stage(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         uint64_t q, uint64_t twoq) {
+                                         const Mod& m) {
     constexpr int half = 1 << (R - 1 - D);
 #pragma unroll
     for (int g = 0; g < (1 << D); ++g) {
         const Twiddle t = ld_tw(tw + ((tw_base << D) + g));
 #pragma unroll
         for (int l = 0; l < half; ++l)
-            ct_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, q, twoq);
+            ct_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, m);
     }
 }
 template <int R, int D>
 __device__ __forceinline__ void gs_stage(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         uint64_t q, uint64_t twoq) {
+                                         const Mod& m) {
     constexpr int half = 1 << (R - 1 - D);
 #pragma unroll
     for (int g = 0; g < (1 << D); ++g) {
         const Twiddle t = ld_tw(tw + ((tw_base << D) + g));
 #pragma unroll
         for (int l = 0; l < half; ++l)
-            gs_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, q, twoq);
+            gs_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, m);
     }
 }
-// the transform's final inverse stage with N^-1 folded in (transformnat-impl.h:600-624):
-// X = (X+Y)*nInv, Y = (X-Y)*(Tinv[1]*nInv), both canonical
+// The four constants (nInv, Shoup(nInv), Tinv[1]*nInv, Shoup(..)) may carry an extra per-limb scalar folded in by
+// the caller (e.g. QHatInvModq ahead of a base conversion): INTT(x) * s costs nothing extra.
+struct LastConst {
+    uint64_t a, as, b, bs;
+};
+__device__ __forceinline__ LastConst last_const(const ModConst& mc, const uint64_t* __restrict__ fold, uint32_t limb) {
+    if (fold)
+        return LastConst{fold[4 * limb], fold[4 * limb + 1], fold[4 * limb + 2], fold[4 * limb + 3]};
+    return LastConst{mc.nInv, mc.nInvS, mc.w1nInv, mc.w1nInvS};
+}
 template <int R>
-__device__ __forceinline__ void gs_last_stage(uint64_t (&x)[1 << R], const ModConst& mc, uint64_t q, uint64_t twoq) {
+__device__ __forceinline__ void gs_last_stage(uint64_t (&x)[1 << R], const LastConst& lc, const Mod& m) {
     constexpr int half = 1 << (R - 1);
 #pragma unroll
     for (int l = 0; l < half; ++l) {
         const uint64_t s = x[l] + x[l + half];
-        const uint64_t e = x[l] - x[l + half] + twoq;
-        x[l]             = shoup(s, mc.nInv, mc.nInvS, q);
-        x[l + half]      = shoup(e, mc.w1nInv, mc.w1nInvS, q);
+        const uint64_t e = x[l] - x[l + half] + m.twoq;
+        x[l]             = shoup(s, lc.a, lc.as, m.q);
+        x[l + half]      = shoup(e, lc.b, lc.bs, m.q);
     }
 }
 
-// R consecutive CT stages
+// R consecutive CT stages, [0,4q) -> [0,4q)
 template <int R>
 __device__ __forceinline__ void ct_round(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         uint64_t q, uint64_t twoq) {
-    ct_stage<R, 0>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 1) ct_stage<R, 1>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 2) ct_stage<R, 2>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 3) ct_stage<R, 3>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 4) ct_stage<R, 4>(x, tw, tw_base, q, twoq);
+                                         const Mod& m) {
+    ct_stage<R, 0>(x, tw, tw_base, m);
+    if constexpr (R > 1) ct_stage<R, 1>(x, tw, tw_base, m);
+    if constexpr (R > 2) ct_stage<R, 2>(x, tw, tw_base, m);
+    if constexpr (R > 3) ct_stage<R, 3>(x, tw, tw_base, m);
+    if constexpr (R > 4) ct_stage<R, 4>(x, tw, tw_base, m);
 }
-// R consecutive GS stages (mirror order).  If LAST, local depth 0 is the transform's final stage.
+// R consecutive GS stages (mirror order), [0,2q) -> [0,2q).  If LAST, depth 0 is the transform's final stage
+// (canonical outputs).
 template <int R, bool LAST>
 __device__ __forceinline__ void gs_round(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         const ModConst& mc, uint64_t q, uint64_t twoq) {
-    if constexpr (R > 4) gs_stage<R, 4>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 3) gs_stage<R, 3>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 2) gs_stage<R, 2>(x, tw, tw_base, q, twoq);
-    if constexpr (R > 1) gs_stage<R, 1>(x, tw, tw_base, q, twoq);
+                                         const LastConst& lc, const Mod& m) {
+    if constexpr (R > 4) gs_stage<R, 4>(x, tw, tw_base, m);
+    if constexpr (R > 3) gs_stage<R, 3>(x, tw, tw_base, m);
+    if constexpr (R > 2) gs_stage<R, 2>(x, tw, tw_base, m);
+    if constexpr (R > 1) gs_stage<R, 1>(x, tw, tw_base, m);
     if constexpr (LAST)
-        gs_last_stage<R>(x, mc, q, twoq);
+        gs_last_stage<R>(x, lc, m);
     else
-        gs_stage<R, 0>(x, tw, tw_base, q, twoq);
+        gs_stage<R, 0>(x, tw, tw_base, m);
 }
 
-__device__ __forceinline__ uint64_t canon4(uint64_t v, uint64_t q, uint64_t twoq) {  // [0,4q) -> [0,q)
-    v = v >= twoq ? v - twoq : v;
-    return v >= q ? v - q : v;
+__device__ __forceinline__ uint64_t canon(uint64_t v, const Mod& m) {  // [0,4q) -> [0,q)
+    v = v >= m.twoq ? v - m.twoq : v;
+    return v >= m.q ? v - m.q : v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,21 +144,22 @@ __global__ void __launch_bounds__(256) ntt_fwd_strided(RingDev r, const uint64_t
     const uint32_t c      = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= stride)
         return;
-    const uint64_t q = r.mc[mi].q, twoq = 2 * q;
+    const Mod m = make_mod(r.mc[mi]);
     const uint64_t* src = in + (size_t)lm.pos[limb] * r.N + c;
     uint64_t* dst       = out + (size_t)op.pos[limb] * r.N + c;
     uint64_t x[1 << A];
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
         x[k] = src[(size_t)k * stride];
-    ct_round<A>(x, r.tw_fwd + (size_t)mi * r.N, 1u, q, twoq);
+    ct_round<A>(x, r.tw_fwd + (size_t)mi * r.N, 1u, m);
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
         dst[(size_t)k * stride] = x[k];  // lazy [0,4q): the tile kernel canonicalises
 }
 
 template <int A>
-__global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data, LimbMap lm) {
+__global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data, LimbMap lm,
+                                                        const uint64_t* __restrict__ fold) {
     const uint32_t limb   = blockIdx.y;
     const uint32_t mi     = lm.idx[limb];
     const uint32_t stride = r.N >> A;
@@ -146,13 +167,13 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data
     if (c >= stride)
         return;
     const ModConst mc = r.mc[mi];
-    const uint64_t q = mc.q, twoq = 2 * q;
+    const Mod m       = make_mod(mc);
     uint64_t* p = data + (size_t)lm.pos[limb] * r.N + c;
     uint64_t x[1 << A];
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
         x[k] = p[(size_t)k * stride];
-    gs_round<A, true>(x, r.tw_inv + (size_t)mi * r.N, 1u, mc, q, twoq);
+    gs_round<A, true>(x, r.tw_inv + (size_t)mi * r.N, 1u, last_const(mc, fold, limb), m);
     // every point passed through the folded last stage => already canonical
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
@@ -166,17 +187,20 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data
 //   round C: tile bits  3..0   thread t holds c = 16t + k               (128 contiguous bytes / thread)
 // Exchange A<->B is conflict-free in linear layout; B<->C uses the swizzle c ^ ((c>>4)&15).
 constexpr int kTile = 4096;
+#ifndef OFHE_TILE_MINB
+#define OFHE_TILE_MINB 3  // resident CTAs per SM the tile kernels are compiled for (register cap 65536/(256*MINB))
+#endif
 __device__ __forceinline__ uint32_t swz(uint32_t c) {
     return c ^ ((c >> 4) & 15u);
 }
 
 template <bool SINGLE>  // SINGLE: logN == 12, input is canonical and no strided kernel ran before
-__global__ void __launch_bounds__(256) ntt_fwd_tile(RingDev r, const uint64_t* in,
+__global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_fwd_tile(RingDev r, const uint64_t* in,
                                                      uint64_t* out, LimbMap lm, PosMap op) {
     __shared__ uint64_t sm[kTile];
     const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
     const uint32_t mi = lm.idx[limb];
-    const uint64_t q = r.mc[mi].q, twoq = 2 * q;
+    const Mod m         = make_mod(r.mc[mi]);
     const Twiddle* tw   = r.tw_fwd + (size_t)mi * r.N;
     const uint32_t s0   = r.logN - 12;  // first stage handled here
     const size_t base   = (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
@@ -186,7 +210,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_tile(RingDev r, const uint64_t* i
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = in[base + t + 256 * k];
-    ct_round<4>(x, tw, (1u << s0) + tile, q, twoq);
+    ct_round<4>(x, tw, (1u << s0) + tile, m);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[t + 256 * k] = x[k];
@@ -196,7 +220,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_tile(RingDev r, const uint64_t* i
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[bh * 256 + bl + 16 * k];
-    ct_round<4>(x, tw, ((1u << s0) + tile) * 16u + bh, q, twoq);
+    ct_round<4>(x, tw, ((1u << s0) + tile) * 16u + bh, m);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -206,21 +230,22 @@ __global__ void __launch_bounds__(256) ntt_fwd_tile(RingDev r, const uint64_t* i
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[swz(16 * t + k)];
-    ct_round<4>(x, tw, ((1u << s0) + tile) * 256u + t, q, twoq);
+    ct_round<4>(x, tw, ((1u << s0) + tile) * 256u + t, m);
     ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + obase + 16 * t);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        dst[k] = make_ulonglong2(canon4(x[2 * k], q, twoq), canon4(x[2 * k + 1], q, twoq));
+        dst[k] = make_ulonglong2(canon(x[2 * k], m), canon(x[2 * k + 1], m));
 }
 
 template <bool SINGLE>  // SINGLE: logN == 12, the folded last stage happens in round A
-__global__ void __launch_bounds__(256) ntt_inv_tile(RingDev r, const uint64_t* in,
-                                                     uint64_t* out, LimbMap lm, PosMap op) {
+__global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_inv_tile(RingDev r, const uint64_t* in,
+                                                     uint64_t* out, LimbMap lm, PosMap op,
+                                                     const uint64_t* __restrict__ fold) {
     __shared__ uint64_t sm[kTile];
     const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
     const uint32_t mi = lm.idx[limb];
     const ModConst mc = r.mc[mi];
-    const uint64_t q = mc.q, twoq = 2 * q;
+    const Mod m       = make_mod(mc);
     const Twiddle* tw = r.tw_inv + (size_t)mi * r.N;
     const uint32_t s0 = r.logN - 12;
     const size_t base = (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
@@ -234,7 +259,8 @@ __global__ void __launch_bounds__(256) ntt_inv_tile(RingDev r, const uint64_t* i
         x[2 * k]     = v.x;
         x[2 * k + 1] = v.y;
     }
-    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 256u + t, mc, q, twoq);
+    const LastConst lc = last_const(mc, SINGLE ? fold : nullptr, limb);
+    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 256u + t, lc, m);  // canonical input
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[swz(16 * t + k)] = x[k];
@@ -244,7 +270,7 @@ __global__ void __launch_bounds__(256) ntt_inv_tile(RingDev r, const uint64_t* i
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[swz(bh * 256 + bl + 16 * k)];
-    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 16u + bh, mc, q, twoq);
+    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 16u + bh, lc, m);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -254,7 +280,7 @@ __global__ void __launch_bounds__(256) ntt_inv_tile(RingDev r, const uint64_t* i
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[t + 256 * k];
-    gs_round<4, SINGLE>(x, tw, (1u << s0) + tile, mc, q, twoq);
+    gs_round<4, SINGLE>(x, tw, (1u << s0) + tile, lc, m);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         out[obase + t + 256 * k] = x[k];  // SINGLE: canonical; else lazy [0,2q), finished by the strided kernel
@@ -264,39 +290,42 @@ __global__ void __launch_bounds__(256) ntt_inv_tile(RingDev r, const uint64_t* i
 // Small rings (N < 4096: the reference's unit-test sizes): one CTA per limb, whole limb in shared memory,
 // one stage per barrier.  Not a performance path.
 template <bool INV>
-__global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap lm, PosMap op) {
+__global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap lm, PosMap op,
+                          const uint64_t* __restrict__ fold) {
     extern __shared__ uint64_t s[];
     const uint32_t limb = lm.pos[blockIdx.x], olimb = op.pos[blockIdx.x], mi = lm.idx[blockIdx.x], N = r.N;
     const ModConst mc = r.mc[mi];
+    const Mod m       = make_mod(mc);
     const uint64_t q = mc.q, twoq = 2 * q;
     const Twiddle* tw = (INV ? r.tw_inv : r.tw_fwd) + (size_t)mi * N;
     for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
         s[i] = in[(size_t)limb * N + i];
     __syncthreads();
     if (!INV) {
-        for (uint32_t m = 1, t = N >> 1; m < N; m <<= 1, t >>= 1) {
+        for (uint32_t mm = 1, t = N >> 1; mm < N; mm <<= 1, t >>= 1) {
             for (uint32_t b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
                 uint32_t i = b / t, j = 2 * i * t + (b % t);
-                ct_bfly(s[j], s[j + t], ld_tw(tw + m + i), q, twoq);
+                ct_bfly(s[j], s[j + t], ld_tw(tw + mm + i), m);
             }
             __syncthreads();
         }
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
-            out[(size_t)olimb * N + i] = canon4(s[i], q, twoq);
+            out[(size_t)olimb * N + i] = canon(s[i], m);
     }
     else {
-        for (uint32_t m = N >> 1, t = 1; m > 1; m >>= 1, t <<= 1) {
+        for (uint32_t mm = N >> 1, t = 1; mm > 1; mm >>= 1, t <<= 1) {
             for (uint32_t b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
                 uint32_t i = b / t, j = 2 * i * t + (b % t);
-                gs_bfly(s[j], s[j + t], ld_tw(tw + m + i), q, twoq);
+                gs_bfly(s[j], s[j + t], ld_tw(tw + mm + i), m);
             }
             __syncthreads();
         }
-        const uint32_t h = N >> 1;
+        const uint32_t h  = N >> 1;
+        const LastConst lc = last_const(mc, fold, blockIdx.x);
         for (uint32_t j = threadIdx.x; j < h; j += blockDim.x) {
             uint64_t a = s[j] + s[j + h], e = s[j] - s[j + h] + twoq;
-            out[(size_t)olimb * N + j]     = shoup(a, mc.nInv, mc.nInvS, q);
-            out[(size_t)olimb * N + j + h] = shoup(e, mc.w1nInv, mc.w1nInvS, q);
+            out[(size_t)olimb * N + j]     = shoup(a, lc.a, lc.as, q);
+            out[(size_t)olimb * N + j + h] = shoup(e, lc.b, lc.bs, q);
         }
     }
 }
@@ -317,12 +346,13 @@ void fwd_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm
     ntt_fwd_tile<false><<<g2, 256, 0, st>>>(r.dev(), out, out, on_output(lm, op), op);
 }
 template <int A>
-void inv_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+void inv_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op,
+             const uint64_t* fold, cudaStream_t st) {
     dim3 g2(r.N / kTile, lm.n);
-    ntt_inv_tile<false><<<g2, 256, 0, st>>>(r.dev(), in, out, lm, op);
+    ntt_inv_tile<false><<<g2, 256, 0, st>>>(r.dev(), in, out, lm, op, nullptr);
     const uint32_t stride = r.N >> A;
     dim3 g1((stride + 255) / 256, lm.n);
-    ntt_inv_strided<A><<<g1, 256, 0, st>>>(r.dev(), out, on_output(lm, op));
+    ntt_inv_strided<A><<<g1, 256, 0, st>>>(r.dev(), out, on_output(lm, op), fold);
 }
 PosMap default_pos(const LimbMap& lm, const PosMap* out_pos) {
     if (out_pos)
@@ -342,7 +372,7 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
     const PosMap op = default_pos(lm, out_pos);
     if (r.logN < 12) {
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
-        ntt_small<false><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op);
+        ntt_small<false><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, nullptr);
     }
     else if (r.logN == 12) {
         ntt_fwd_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op);
@@ -361,24 +391,24 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
 }
 
 void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
-                    const PosMap* out_pos) {
+                    const PosMap* out_pos, const uint64_t* fold) {
     if (lm.n == 0)
         return;
     const PosMap op = default_pos(lm, out_pos);
     if (r.logN < 12) {
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
-        ntt_small<true><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op);
+        ntt_small<true><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, fold);
     }
     else if (r.logN == 12) {
-        ntt_inv_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op);
+        ntt_inv_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op, fold);
     }
     else {
         switch (r.logN - 12) {
-            case 1: inv_big<1>(r, in, out, lm, op, st); break;
-            case 2: inv_big<2>(r, in, out, lm, op, st); break;
-            case 3: inv_big<3>(r, in, out, lm, op, st); break;
-            case 4: inv_big<4>(r, in, out, lm, op, st); break;
-            case 5: inv_big<5>(r, in, out, lm, op, st); break;
+            case 1: inv_big<1>(r, in, out, lm, op, fold, st); break;
+            case 2: inv_big<2>(r, in, out, lm, op, fold, st); break;
+            case 3: inv_big<3>(r, in, out, lm, op, fold, st); break;
+            case 4: inv_big<4>(r, in, out, lm, op, fold, st); break;
+            case 5: inv_big<5>(r, in, out, lm, op, fold, st); break;
             default: throw Error("ring dimension above 2^17 is not supported");
         }
     }

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libofhe_b200.so")
+LIB_PATH = os.environ.get("OFHE_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libofhe_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "ofhe_b200.h")
 
 _u64p = C.POINTER(C.c_uint64)
