@@ -42,6 +42,7 @@ int ofhe_malloc(ofhe_ctx* ctx, size_t bytes, void** dptr);
 int ofhe_free(ofhe_ctx* ctx, void* dptr);
 int ofhe_memcpy_h2d(ofhe_ctx* ctx, void* dst_d, const void* src_h, size_t bytes, void* stream);
 int ofhe_memcpy_d2h(ofhe_ctx* ctx, void* dst_h, const void* src_d, size_t bytes, void* stream);
+int ofhe_memcpy_d2d(ofhe_ctx* ctx, void* dst_d, const void* src_d, size_t bytes, void* stream);
 int ofhe_stream_sync(ofhe_ctx* ctx, void* stream);
 
 /* ---- ring: replaces ILDCRTParams + the static twiddle caches

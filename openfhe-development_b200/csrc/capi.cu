@@ -114,6 +114,12 @@ int ofhe_memcpy_d2h(ofhe_ctx* ctx, void* h, const void* d, size_t bytes, void* s
         OFHE_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, S(stream)));
     });
 }
+int ofhe_memcpy_d2d(ofhe_ctx* ctx, void* d, const void* s, size_t bytes, void* stream) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+    });
+}
 int ofhe_stream_sync(ofhe_ctx* ctx, void* stream) {
     return guard([&] {
         OFHE_CUDA(cudaSetDevice(ctx->c->device));

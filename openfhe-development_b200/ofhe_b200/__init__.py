@@ -29,6 +29,7 @@ SIGNATURES = {
     "ofhe_free": (C.c_int, [_vp, _vp]),
     "ofhe_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ofhe_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "ofhe_memcpy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ofhe_stream_sync": (C.c_int, [_vp, _vp]),
     "ofhe_ring_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp)]),
     "ofhe_ring_destroy": (None, [_vp]),
