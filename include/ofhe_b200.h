@@ -155,6 +155,28 @@ uint64_t ofhe_last_prime(uint32_t bits, uint64_t m);         /* LastPrime     :3
 uint64_t ofhe_previous_prime(uint64_t q, uint64_t m);        /* PreviousPrime :385-393 */
 uint64_t ofhe_next_prime(uint64_t q, uint64_t m);            /* NextPrime     :375-383 */
 
+/* ---- limb-sharded EvalMult across `world` ranks (one GPU each), SURVEY.md 8(e).  Q limb i lives on rank i mod world
+ *      (local row i div world), P limb j on rank (j + sizeQ) mod world (local row j div world).  Per rank:
+ *        ct*_d / out_d   [2][nOwnQ][N]                local rows of the ciphertexts
+ *        evk_a_d/evk_b_d [dnum][nKeyRows][N]          local rows of the key (owned Q rows of the FULL Q, then owned P rows)
+ *        gatherQ_d       [world][slotsQ][N]           all-gather buffer (this rank writes rows rank*slotsQ ...)
+ *        gatherP_d       [world][2][slotsP][N]        all-gather buffer (this rank writes rows (rank*2+b)*slotsP ...)
+ *      Call a, all-gather gatherQ in place, call b, all-gather gatherP in place, call c.  The collectives are the
+ *      caller's (NCCL): they replace nothing in the reference, which is single-process.        */
+typedef struct ofhe_shard ofhe_shard;
+int ofhe_shard_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeP, uint32_t numPartQ, uint32_t rank, uint32_t world,
+                      ofhe_shard** out);
+void ofhe_shard_destroy(ofhe_shard* s);
+/* info_out: nOwnQ(sizeQl), nOwnP, slotsQ(sizeQl), slotsP, nKeyRows, numDigits(sizeQl) */
+int ofhe_shard_info(ofhe_shard* s, uint32_t sizeQl, uint32_t* info_out);
+/* owned limb indices at this level: q_idx_out[nOwnQ] (indices into Q), p_idx_out[nOwnP] (indices into P) */
+int ofhe_shard_owned(ofhe_shard* s, uint32_t sizeQl, uint32_t* q_idx_out, uint32_t* p_idx_out);
+int ofhe_shard_evalmult_a(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct1_d, const uint64_t* ct2_d, uint64_t* out_d,
+                          uint64_t* gatherQ_d, void* stream);
+int ofhe_shard_evalmult_b(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gatherQ_d, const uint64_t* evk_a_d,
+                          const uint64_t* evk_b_d, uint64_t* gatherP_d, void* stream);
+int ofhe_shard_evalmult_c(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gatherP_d, uint64_t* out_d, void* stream);
+
 /* fills dst_d [n_limbs][N] with uniform residues in [0, q_l) from a counter-based generator (synthetic inputs) */
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
                       void* stream);

@@ -5,6 +5,7 @@
 #include "../../include/ofhe_b200.h"
 #include "hks.h"
 #include "hostmath.h"
+#include "shard.h"
 
 using namespace ofhe;
 
@@ -25,6 +26,9 @@ struct ofhe_hks {
 };
 struct ofhe_evk {
     EvalKey* k;
+};
+struct ofhe_shard {
+    Shard* s;
 };
 
 namespace {
@@ -549,6 +553,63 @@ uint64_t ofhe_previous_prime(uint64_t q, uint64_t m) {
 }
 uint64_t ofhe_next_prime(uint64_t q, uint64_t m) {
     return hm::next_prime(q, m);
+}
+
+int ofhe_shard_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeP, uint32_t numPartQ, uint32_t rank, uint32_t world,
+                      ofhe_shard** out) {
+    return guard([&] {
+        OFHE_REQUIRE(ring && out, "null argument");
+        use(ring->r);
+        *out = new ofhe_shard{new Shard(ring->r, sizeQ, sizeP, numPartQ, rank, world)};
+    });
+}
+void ofhe_shard_destroy(ofhe_shard* s) {
+    if (s) {
+        delete s->s;
+        delete s;
+    }
+}
+int ofhe_shard_info(ofhe_shard* s, uint32_t sizeQl, uint32_t* o) {
+    return guard([&] {
+        use(s->s->ring);
+        Shard::Level& lv = s->s->level(sizeQl);
+        o[0] = lv.nOwnQ;
+        o[1] = (uint32_t)s->s->ownP.size();
+        o[2] = lv.slotsQ;
+        o[3] = s->s->slotsP;
+        o[4] = s->s->nOwnQFull + (uint32_t)s->s->ownP.size();
+        o[5] = lv.n_digits;
+    });
+}
+int ofhe_shard_owned(ofhe_shard* s, uint32_t sizeQl, uint32_t* q, uint32_t* p) {
+    return guard([&] {
+        use(s->s->ring);
+        Shard::Level& lv = s->s->level(sizeQl);
+        for (size_t t = 0; t < lv.ownQ.size(); ++t)
+            q[t] = lv.ownQ[t];
+        for (size_t t = 0; t < s->s->ownP.size(); ++t)
+            p[t] = s->s->ownP[t];
+    });
+}
+int ofhe_shard_evalmult_a(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct1_d, const uint64_t* ct2_d, uint64_t* out_d,
+                          uint64_t* gatherQ_d, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        s->s->evalmult_a(sizeQl, ct1_d, ct2_d, out_d, gatherQ_d, S(stream));
+    });
+}
+int ofhe_shard_evalmult_b(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gatherQ_d, const uint64_t* evk_a_d,
+                          const uint64_t* evk_b_d, uint64_t* gatherP_d, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        s->s->evalmult_b(sizeQl, gatherQ_d, evk_a_d, evk_b_d, gatherP_d, S(stream));
+    });
+}
+int ofhe_shard_evalmult_c(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gatherP_d, uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        s->s->evalmult_c(sizeQl, gatherP_d, out_d, S(stream));
+    });
 }
 
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,

@@ -20,8 +20,6 @@
 
 namespace ofhe {
 
-namespace {
-
 std::unique_ptr<BConv> make_bconv(const Ring& r, const std::vector<uint32_t>& src_idx,
                                   const std::vector<uint32_t>& src_pos, const std::vector<uint32_t>& dst_idx,
                                   const std::vector<uint32_t>& dst_pos) {
@@ -64,6 +62,8 @@ std::unique_ptr<BConv> make_bconv(const Ring& r, const std::vector<uint32_t>& sr
     OFHE_CUDA(cudaMemcpy(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size(), cudaMemcpyHostToDevice));
     return t;
 }
+
+namespace {
 
 void fill_scalar(ScalarVec& sv, uint32_t i, uint64_t s, uint64_t q) {
     sv.s[i]  = s;

@@ -1,0 +1,52 @@
+// shard.h -- limb-sharded CKKS EvalMult / hybrid key switch (one rank's share).  See shard.cu.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace ofhe {
+
+struct Shard {
+    Ring* ring;
+    uint32_t sizeQ, sizeP, dnum, alpha, rank, world;
+    uint32_t slotsP = 0, nOwnQFull = 0;
+    std::vector<uint32_t> ownP;  // owned P limb indices (0-based within P), ascending
+
+    uint32_t owner_q(uint32_t i) const { return i % world; }
+    uint32_t owner_p(uint32_t j) const { return (j + sizeQ) % world; }
+
+    struct Level {
+        uint32_t slotsQ = 0, nOwnQ = 0, n_digits = 0;
+        std::vector<uint32_t> ownQ;
+        LimbMap map_q, map_qp, map_q2, map_p2_src, map_modup_ntt;
+        PosMap gatherq_pos, gatherp_pos;
+        std::vector<std::unique_ptr<BConv>> modup;
+        std::vector<uint32_t> own_first, own_count;  // owned rows of each digit (contiguous local rows)
+        std::unique_ptr<BConv> moddown;
+        uint64_t* fold_q_d = nullptr;
+        uint64_t* fold_p_d = nullptr;
+        ScalarVec pinv;
+        ~Level();
+    };
+    std::map<uint32_t, std::unique_ptr<Level>> levels;
+    std::mutex mu;
+
+    Shard(Ring* r, uint32_t sizeQ, uint32_t sizeP, uint32_t dnum, uint32_t rank, uint32_t world);
+    ~Shard();
+    Level& level(uint32_t sizeQl);
+    size_t workspace_words(uint32_t sizeQl);
+    // phase A: tensor product on the owned limbs (out = c0 | c1), INTT(c2) * QHatInv into this rank's rows of gatherQ
+    void evalmult_a(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out, uint64_t* gatherQ,
+                    cudaStream_t st);
+    // phase B (after the all-gather of gatherQ): ModUp into the owned rows, NTT, evk inner product, INTT of the owned
+    // P rows * PHatInv into this rank's rows of gatherP
+    void evalmult_b(uint32_t sizeQl, const uint64_t* gatherQ, const uint64_t* evk_a, const uint64_t* evk_b,
+                    uint64_t* gatherP, cudaStream_t st);
+    // phase C (after the all-gather of gatherP): ModDown of the owned Q rows and the final additions into out
+    void evalmult_c(uint32_t sizeQl, const uint64_t* gatherP, uint64_t* out, cudaStream_t st);
+};
+
+}  // namespace ofhe

@@ -66,6 +66,13 @@ SIGNATURES = {
     "ofhe_last_prime": (C.c_uint64, [C.c_uint32, C.c_uint64]),
     "ofhe_previous_prime": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "ofhe_next_prime": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "ofhe_shard_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "ofhe_shard_destroy": (None, [_vp]),
+    "ofhe_shard_info": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "ofhe_shard_owned": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "ofhe_shard_evalmult_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_evalmult_b": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_evalmult_c": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "ofhe_fill_uniform": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp]),
 }
 
@@ -312,3 +319,63 @@ class Hks:
 
     def rotate(self, sizeQl, k, ct, evk, out):
         _ck(lib().ofhe_ckks_rotate(self.h, sizeQl, k, _ptr(ct), evk.h, _ptr(out), _stream()))
+
+
+# ---- limb-sharded EvalMult (SURVEY.md 8 e) --------------------------------------------------------------------------
+def shard_plan(sizeQ, sizeP, sizeQl, world, rank):
+    """Ownership of the limb-sharded layout (pure host logic, mirrored by csrc/shard.cu and checked against it):
+    Q limb i -> rank i % world, local row i // world; P limb j -> rank (j + sizeQ) % world, local row j // world."""
+    own_q = [i for i in range(sizeQl) if i % world == rank]
+    own_q_full = [i for i in range(sizeQ) if i % world == rank]
+    own_p = [j for j in range(sizeP) if (j + sizeQ) % world == rank]
+    return dict(own_q=own_q, own_p=own_p, own_q_full=own_q_full, slots_q=-(-sizeQl // world), slots_p=-(-sizeP // world),
+                n_key_rows=len(own_q_full) + len(own_p),
+                gather_q_row=lambda i: (i % world) * (-(-sizeQl // world)) + i // world,
+                gather_p_row=lambda j, b: (((j + sizeQ) % world) * 2 + b) * (-(-sizeP // world)) + j // world)
+
+
+class Shard:
+    """One rank's share of a limb-sharded CKKS EvalMult.  `all_gather(buf)` is supplied by the caller: in place on a
+    [world, ...] tensor (torch.distributed.all_gather_into_tensor over NCCL in production; a local copy loop in the
+    single-GPU virtual-rank tests)."""
+
+    def __init__(self, ring, sizeQ, sizeP, dnum, rank, world):
+        self.ring, self.sizeQ, self.sizeP, self.dnum, self.rank, self.world = ring, sizeQ, sizeP, dnum, rank, world
+        h = _vp()
+        _ck(lib().ofhe_shard_create(ring.h, sizeQ, sizeP, dnum, rank, world, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().ofhe_shard_destroy(self.h)
+            self.h = None
+
+    def info(self, sizeQl):
+        o = np.zeros(6, dtype=np.uint32)
+        _ck(lib().ofhe_shard_info(self.h, sizeQl, o.ctypes.data))
+        return dict(n_own_q=int(o[0]), n_own_p=int(o[1]), slots_q=int(o[2]), slots_p=int(o[3]), n_key_rows=int(o[4]),
+                    n_digits=int(o[5]))
+
+    def owned(self, sizeQl):
+        i = self.info(sizeQl)
+        q = np.zeros(max(i["n_own_q"], 1), dtype=np.uint32)
+        p = np.zeros(max(i["n_own_p"], 1), dtype=np.uint32)
+        _ck(lib().ofhe_shard_owned(self.h, sizeQl, q.ctypes.data, p.ctypes.data))
+        return q[:i["n_own_q"]].tolist(), p[:i["n_own_p"]].tolist()
+
+    def phase_a(self, sizeQl, ct1, ct2, out, gather_q):
+        _ck(lib().ofhe_shard_evalmult_a(self.h, sizeQl, _ptr(ct1), _ptr(ct2), _ptr(out), _ptr(gather_q), _stream()))
+
+    def phase_b(self, sizeQl, gather_q, evk_a, evk_b, gather_p):
+        _ck(lib().ofhe_shard_evalmult_b(self.h, sizeQl, _ptr(gather_q), _ptr(evk_a), _ptr(evk_b), _ptr(gather_p),
+                                        _stream()))
+
+    def phase_c(self, sizeQl, gather_p, out):
+        _ck(lib().ofhe_shard_evalmult_c(self.h, sizeQl, _ptr(gather_p), _ptr(out), _stream()))
+
+    def evalmult(self, sizeQl, ct1, ct2, evk_a, evk_b, out, gather_q, gather_p, all_gather):
+        self.phase_a(sizeQl, ct1, ct2, out, gather_q)
+        all_gather(gather_q)
+        self.phase_b(sizeQl, gather_q, evk_a, evk_b, gather_p)
+        all_gather(gather_p)
+        self.phase_c(sizeQl, gather_p, out)

@@ -1,0 +1,91 @@
+"""Limb-sharded EvalMult (SURVEY.md 8 e): G virtual ranks on ONE GPU (each with its own context / scratch, the
+all-gathers emulated by device copies) must reproduce the unsharded device result -- which test_gpu_parity.py pins to
+the oracle / reference -- bit for bit.  The real NCCL path is tests/test_gpu_multi.py (needs >= 2 GPUs)."""
+import numpy as np
+import pytest
+
+from oracle_lib import seeded_residues
+
+pytestmark = pytest.mark.gpu
+
+
+def run_virtual(m, ctx0, p, world, sizeQl, ct1, ct2, ea, eb):
+    """Returns the full [2][sizeQl][N] result assembled from the ranks' local rows."""
+    import torch
+
+    N, sizeQ, sizeP, dnum = p["N"], p["sizeQ"], p["sizeP"], p["dnum"]
+    ranks = []
+    for r in range(world):
+        ctx = m.Context(0)
+        ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+        sh = m.Shard(ring, sizeQ, sizeP, dnum, r, world)
+        info = sh.info(sizeQl)
+        own_q, own_p = sh.owned(sizeQl)
+        plan = m.shard_plan(sizeQ, sizeP, sizeQl, world, r)
+        assert own_q == plan["own_q"] and own_p == plan["own_p"]
+        assert (info["slots_q"], info["slots_p"], info["n_key_rows"]) == (plan["slots_q"], plan["slots_p"], plan["n_key_rows"])
+        key_rows = plan["own_q_full"] + [sizeQ + j for j in own_p]
+        d = dict(ctx=ctx, ring=ring, sh=sh, info=info, own_q=own_q,
+                 ct1=ctx.upload(ct1[:, own_q]) if own_q else ctx.zeros(2, 0, N),
+                 ct2=ctx.upload(ct2[:, own_q]) if own_q else ctx.zeros(2, 0, N),
+                 out=ctx.zeros(2, len(own_q), N),
+                 ea=ctx.upload(ea[:, key_rows]), eb=ctx.upload(eb[:, key_rows]),
+                 gq=ctx.zeros(world, info["slots_q"], N), gp=ctx.zeros(world, 2, info["slots_p"], N))
+        ranks.append(d)
+
+    def exchange(key):
+        torch.cuda.synchronize()
+        for src in range(world):
+            for dst in range(world):
+                if dst != src:
+                    ranks[dst][key][src].copy_(ranks[src][key][src])
+        torch.cuda.synchronize()
+
+    for d in ranks:
+        d["sh"].phase_a(sizeQl, d["ct1"], d["ct2"], d["out"], d["gq"])
+    exchange("gq")
+    for d in ranks:
+        d["sh"].phase_b(sizeQl, d["gq"], d["ea"], d["eb"], d["gp"])
+    exchange("gp")
+    for d in ranks:
+        d["sh"].phase_c(sizeQl, d["gp"], d["out"])
+    torch.cuda.synchronize()
+    full = np.zeros((2, sizeQl, N), dtype=np.uint64)
+    for d in ranks:
+        if d["own_q"]:
+            full[:, d["own_q"]] = ctx0.download(d["out"])
+    for d in ranks:
+        d["sh"].close()
+        d["ring"].close()
+        d["ctx"].close()
+    return full
+
+
+@pytest.mark.parametrize("args,worlds", [((1 << 12, 8, 50, 60, 3, 0), (1, 2, 3, 8)), ((1 << 13, 5, 59, 60, 2, 0), (2, 4)),
+                                         ((1 << 12, 2, 45, 55, 0, 0), (2, 8))])
+def test_virtual_ranks_match_unsharded(gpu, oracle, args, worlds):
+    ctx, m = gpu
+    p = m.ckks_paramgen(*args)
+    N, sizeQ, sizeP, dnum = p["N"], p["sizeQ"], p["sizeP"], p["dnum"]
+    ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+    hks = m.Hks(ring, sizeQ, sizeP, dnum)
+    ea = seeded_residues(81, np.tile(p["moduli"], dnum), N).reshape(dnum, sizeQ + sizeP, N)
+    eb = seeded_residues(82, np.tile(p["moduli"], dnum), N).reshape(dnum, sizeQ + sizeP, N)
+    evk = m.EvalKey(hks, ea, eb)
+    for sizeQl in sorted({sizeQ, max(1, sizeQ - 1), 1}, reverse=True):
+        ct1 = np.stack([seeded_residues(83, p["moduli"][:sizeQl], N), seeded_residues(84, p["moduli"][:sizeQl], N)])
+        ct2 = np.stack([seeded_residues(85, p["moduli"][:sizeQl], N), seeded_residues(86, p["moduli"][:sizeQl], N)])
+        out = ctx.zeros(2, sizeQl, N)
+        hks.evalmult(sizeQl, ctx.upload(ct1), ctx.upload(ct2), evk, out)
+        want = ctx.download(out).copy()
+        if sizeQl == sizeQ:  # anchor the unsharded result to the oracle once per context
+            c = oracle.ckks(*args)
+            try:
+                assert (want == c.evalmult(sizeQl, ct1, ct2, ea, eb)).all()
+            finally:
+                c.close()
+        for world in worlds:
+            got = run_virtual(m, ctx, p, world, sizeQl, ct1, ct2, ea, eb)
+            assert (got == want).all(), f"world={world} sizeQl={sizeQl}"
+    for o in (evk, hks, ring):
+        o.close()
