@@ -14,7 +14,8 @@ firstModSize 60, HYBRID with dnum 3.  Prints ONE JSON line (rank 0).
                than L2: algorithmic bytes 16*N per limb-NTT / CUDA-event time vs the measured HBM peak
   cpu_baseline the unmodified reference (oracle/_ref) -- or the C oracle port if that build is absent -- timed on
                this box's host cores on a bounded sample of the same workload
-Multi-GPU (round 1): independent ciphertext pairs per rank (replicas, no collective on the data path) -> "weak".
+Multi-GPU: ONE multiplication is sharded by RNS limb over the ranks (north_star / SURVEY 8 e) with two NCCL
+all-gathers per step; total work per step is fixed -> "strong".
 """
 import argparse
 import json
@@ -131,7 +132,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(a.steps, 8))
+        steps = max(1, min(a.steps, 50))
         base, sec = cpu_reference_run(steps, max(1, min(a.warmup, 2)))
         line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=steps,
                     warmup=max(1, min(a.warmup, 2)), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
@@ -156,59 +157,134 @@ def main():
     N, sizeQ, sizeP, dnum = p["N"], p["sizeQ"], p["sizeP"], p["dnum"]
     ctx = m.Context(local_rank)
     ring = m.Ring(ctx, N, p["moduli"], p["roots"])
-    hks = m.Hks(ring, sizeQ, sizeP, dnum)
-    evk = m.EvalKey(hks, seed=1234 + rank)
     sizeQl = sizeQ
-    idx2 = list(range(sizeQl)) * 2
-    ct1, ct2, out = ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N)
-    ring.fill_uniform(ct1.view(2 * sizeQl, N), idx2, 11 + rank)
-    ring.fill_uniform(ct2.view(2 * sizeQl, N), idx2, 12 + rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ----------------------------------------------------------------------------
-    for _ in range(a.warmup):
-        hks.evalmult(sizeQl, ct1, ct2, evk, out)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        hks.evalmult(sizeQl, ct1, ct2, evk, out)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    sampler.stop_flag.set()
-    t = torch.tensor([ms], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * a.steps / (ms * 1e-3)
+    def max_over_ranks(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- end to end through the host-buffer entry point (pinned host memory, copies inside the timed region) ----
-    h1 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
-    h2 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
-    ho = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
-    h1.copy_(ct1.cpu())
-    h2.copy_(ct2.cpu())
-    e2e_steps = max(3, min(a.steps, 10))
-    for _ in range(2):
-        hks.evalmult_host(sizeQl, h1, h2, evk, ho)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hks.evalmult_host(sizeQl, h1, h2, evk, ho)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    assert bool((ho.cuda() == out).all()), "host-buffer path and device path disagree"
+    sampler = ClockSampler(local_rank)
+    if world == 1:
+        hks = m.Hks(ring, sizeQ, sizeP, dnum)
+        evk = m.EvalKey(hks, seed=1234)
+        idx2 = list(range(sizeQl)) * 2
+        ct1, ct2, out = ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N)
+        ring.fill_uniform(ct1.view(2 * sizeQl, N), idx2, 11)
+        ring.fill_uniform(ct2.view(2 * sizeQl, N), idx2, 12)
+        # ---- device-resident throughput ------------------------------------------------------------------------
+        for _ in range(a.warmup):
+            hks.evalmult(sizeQl, ct1, ct2, evk, out)
+        barrier()
+        sampler.start()
+        e0.record()
+        for _ in range(a.steps):
+            hks.evalmult(sizeQl, ct1, ct2, evk, out)
+        e1.record()
+        barrier()
+        sampler.stop_flag.set()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        value = a.steps / (ms * 1e-3)
+        parallelism, scaling, launches = "single GPU", "weak", LAUNCHES_PER_STEP
+        # ---- end to end through the host-buffer entry point (pinned host memory, copies inside the timed region)
+        h1 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
+        h2 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
+        ho = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
+        h1.copy_(ct1.cpu())
+        h2.copy_(ct2.cpu())
+        e2e_steps = max(3, min(a.steps, 10))
+        for _ in range(2):
+            hks.evalmult_host(sizeQl, h1, h2, evk, ho)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hks.evalmult_host(sizeQl, h1, h2, evk, ho)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        assert bool((ho.cuda() == out).all()), "host-buffer path and device path disagree"
+        closers = [evk, hks]
+    else:
+        # ---- limb-sharded across the ranks (SURVEY 8 e): one EvalMult is split by RNS limb; two NCCL all-gathers per
+        #      step (ModUp sources, ModDown P limbs).  Two pipeline slots on two streams let the all-gathers of one
+        #      multiplication overlap the kernels of the next (steps are independent ciphertext pairs).
+        n_slots = 2
+        shards = [m.Shard(ring, sizeQ, sizeP, dnum, rank, world) for _ in range(n_slots)]
+        info = shards[0].info(sizeQl)
+        own_q, own_p = shards[0].owned(sizeQl)
+        nq = len(own_q)
+        key_idx = [i for i in range(sizeQ) if i % world == rank] + [sizeQ + j for j in own_p]
+        ea, eb = ctx.zeros(dnum, len(key_idx), N), ctx.zeros(dnum, len(key_idx), N)
+        for j in range(dnum):
+            ring.fill_uniform(ea[j], key_idx, 1000 + 2 * j)
+            ring.fill_uniform(eb[j], key_idx, 1001 + 2 * j)
+        ct1, ct2 = ctx.zeros(2, nq, N), ctx.zeros(2, nq, N)
+        ring.fill_uniform(ct1.view(2 * nq, N), own_q * 2, 11)
+        ring.fill_uniform(ct2.view(2 * nq, N), own_q * 2, 12)
+        outs = [ctx.zeros(2, nq, N) for _ in range(n_slots)]
+        gqs = [ctx.zeros(world, info["slots_q"], N) for _ in range(n_slots)]
+        gps = [ctx.zeros(world, 2, info["slots_p"], N) for _ in range(n_slots)]
+        streams = [torch.cuda.Stream() for _ in range(n_slots)]
+
+        def all_gather(buf):
+            dist.all_gather_into_tensor(buf, buf[rank])  # in place: the send segment is this rank's slice of buf
+
+        def step(k):
+            s = k % n_slots
+            with torch.cuda.stream(streams[s]):
+                shards[s].evalmult(sizeQl, ct1, ct2, ea, eb, outs[s], gqs[s], gps[s], all_gather)
+
+        def run(nsteps):
+            cur = torch.cuda.current_stream()
+            for st in streams:
+                st.wait_stream(cur)
+            for k in range(nsteps):
+                step(k)
+            for st in streams:
+                cur.wait_stream(st)
+
+        run(max(a.warmup, n_slots))
+        barrier()
+        sampler.start()
+        e0.record()
+        run(a.steps)
+        e1.record()
+        barrier()
+        sampler.stop_flag.set()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        value = a.steps / (ms * 1e-3)
+        parallelism, scaling = f"RNS limbs sharded over {world} GPUs, 2 NCCL all-gathers per EvalMult, 2 pipeline slots", "strong"
+        launches = LAUNCHES_PER_STEP
+        # ---- end to end: every rank moves its own limb rows host<->device around the sharded multiplication
+        h1 = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
+        h2 = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
+        ho = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
+        h1.copy_(ct1.cpu())
+        h2.copy_(ct2.cpu())
+        d1, d2 = torch.empty_like(ct1), torch.empty_like(ct2)
+        e2e_steps = max(3, min(a.steps, 10))
+
+        def e2e_step():
+            d1.copy_(h1, non_blocking=True)
+            d2.copy_(h2, non_blocking=True)
+            shards[0].evalmult(sizeQl, d1, d2, ea, eb, outs[0], gqs[0], gps[0], all_gather)
+            ho.copy_(outs[0], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        closers = shards
     ct_bytes = 2 * sizeQl * N * 8
 
     # ---- roofline of the dominant kernel family: forward limb-NTT on a slab larger than L2 ---------------------
@@ -239,16 +315,16 @@ def main():
         if not a.no_cpu_baseline:
             base, _ = cpu_reference_run(a.cpu_steps, 1)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64",
+                    ms_per_step=ms / a.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="u64",
                     data="synthetic",
-                    config={"workload": WORKLOAD, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                    config={"workload": WORKLOAD, "parallelism": parallelism,
                             "l2": "per-step working set ~0.6 GB (evk 180 MiB + digits 90 MiB + ...) exceeds the 126 MB L2"},
-                    e2e=dict(value=world * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=2 * ct_bytes,
+                    e2e=dict(value=e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=2 * ct_bytes,
                              d2h_bytes_per_step=ct_bytes, steps=e2e_steps),
-                    gpu_launches=LAUNCHES_PER_STEP * a.steps, roofline=roofline, cpu_baseline=base,
+                    gpu_launches=launches * a.steps, roofline=roofline, cpu_baseline=base,
                     clocks=sampler.summary())
         print(json.dumps(line))
-    for o in (evk, hks, ring, ctx):
+    for o in closers + [ring, ctx]:
         o.close()
     if dist is not None:
         dist.barrier()

@@ -47,7 +47,23 @@ Shard::Shard(Ring* r, uint32_t sizeQ_, uint32_t sizeP_, uint32_t dnum_, uint32_t
     for (uint32_t i = 0; i < sizeQ; ++i)
         nOwnQFull += owner_q(i) == rank;
 }
-Shard::~Shard() = default;
+Shard::~Shard() {
+    if (ws_d)
+        cudaFree(ws_d);
+}
+uint64_t* Shard::scratch(uint32_t sizeQl) {
+    const size_t need = workspace_words(sizeQl);
+    if (need > ws_words) {
+        if (ws_d) {
+            OFHE_CUDA(cudaDeviceSynchronize());
+            OFHE_CUDA(cudaFree(ws_d));
+            ws_d = nullptr;
+        }
+        OFHE_CUDA(cudaMalloc(&ws_d, sizeof(uint64_t) * need));
+        ws_words = need;
+    }
+    return ws_d;
+}
 Shard::Level::~Level() {
     if (fold_q_d)
         cudaFree(fold_q_d);
@@ -178,7 +194,7 @@ void Shard::evalmult_a(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, P = (size_t)lv.nOwnQ * N;
-    uint64_t* ws   = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * workspace_words(sizeQl)));
+    uint64_t* ws   = scratch(sizeQl);
     uint64_t* c2   = ws;
     if (lv.nOwnQ == 0)
         return;
@@ -191,7 +207,7 @@ void Shard::evalmult_b(uint32_t sizeQl, const uint64_t* gatherQ, const uint64_t*
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, nq = lv.nOwnQ, np = ownP.size(), nown = nq + np;
-    uint64_t* ws     = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * workspace_words(sizeQl)));
+    uint64_t* ws     = scratch(sizeQl);
     uint64_t* c2     = ws;
     uint64_t* digits = c2 + nq * N;
     uint64_t* e01    = digits + (size_t)dnum * nown * N;
@@ -219,7 +235,7 @@ void Shard::evalmult_c(uint32_t sizeQl, const uint64_t* gatherP, uint64_t* out, 
     const size_t N = r.N, nq = lv.nOwnQ, np = ownP.size(), nown = nq + np;
     if (nq == 0)
         return;
-    uint64_t* ws     = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * workspace_words(sizeQl)));
+    uint64_t* ws     = scratch(sizeQl);
     uint64_t* digits = ws + nq * N;
     uint64_t* e01    = digits + (size_t)dnum * nown * N;
     uint64_t* conv   = e01 + 2 * nown * N;

@@ -33,6 +33,9 @@ struct Shard {
     };
     std::map<uint32_t, std::unique_ptr<Level>> levels;
     std::mutex mu;
+    uint64_t* ws_d = nullptr;  // scratch owned by THIS object, so several shards (pipeline slots) can be in flight
+    size_t ws_words = 0;
+    uint64_t* scratch(uint32_t sizeQl);
 
     Shard(Ring* r, uint32_t sizeQ, uint32_t sizeP, uint32_t dnum, uint32_t rank, uint32_t world);
     ~Shard();
