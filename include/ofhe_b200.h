@@ -87,6 +87,31 @@ int ofhe_automorphism_map_host(ofhe_ring* ring, uint32_t k, uint32_t* map_h);
 int ofhe_approx_switch_crt_basis(ofhe_ring* ring, uint32_t n_src, const uint32_t* src_idx_h, uint32_t n_dst,
                                  const uint32_t* dst_idx_h, const uint64_t* in_d, uint64_t* out_d, void* stream);
 
+/* ---- table-driven base conversions: the caller supplies the reference's precomputed tables (a20) verbatim.
+ * a10 DCRTPolyImpl::ApproxSwitchCRTBasis with explicit tables      dcrtpoly-impl.h:888-932   (alphaQModp_h == NULL)
+ *     e.g. the first half of FastExpandCRTBasisPloverQ              dcrtpoly-impl.h:1151-1164
+ * a12 DCRTPolyImpl::SwitchCRTBasis (exact, HPS)                     dcrtpoly-impl.h:1008-1085 (alphaQModp_h, qInv_h given)
+ *     used by ExpandCRTBasis                                        dcrtpoly-impl.h:1088-1116
+ *   QHatModp_h is [n_dst][n_src] if table_is_dst_major (the order SwitchCRTBasis takes), else [n_src][n_dst]
+ *   (the order ApproxSwitchCRTBasis takes); alphaQModp_h is [n_src+1][n_dst]; qInv_h is [n_src] doubles.
+ *   The overflow estimate nu = 0.5 + sum double(y_i)*qInv[i] is evaluated in index order with separately rounded
+ *   IEEE multiply and add (no FMA), so (size_t)nu equals the reference's on every coefficient.
+ *   apply: in_d [n_src][N] COEFFICIENT -> out_d [n_dst][N] COEFFICIENT                                            */
+typedef struct ofhe_bconv ofhe_bconv;
+int ofhe_bconv_create(ofhe_ring* ring, uint32_t n_src, const uint32_t* src_idx_h, const uint64_t* QHatInvModq_h,
+                      uint32_t n_dst, const uint32_t* dst_idx_h, const uint64_t* QHatModp_h, int table_is_dst_major,
+                      const uint64_t* alphaQModp_h, const double* qInv_h, ofhe_bconv** out);
+/* a13 DCRTPolyImpl::ScaleAndRound (DCRT -> DCRT)                    dcrtpoly-impl.h:1513-1628
+ *   input slab in_d [sizeI + sizeO][N] COEFFICIENT: the sizeO limbs of the output basis come first if
+ *   out_limbs_first (output modulus == first input modulus), else last.  in_idx_h[sizeI] / out_idx_h[sizeO] are the
+ *   ring indices of the scaled-away and of the surviving limbs; tbl_h is tOSHatInvModsDivsModo [sizeO][sizeI+1],
+ *   frac_h is tOSHatInvModsDivsFrac [sizeI].  apply: in_d -> out_d [sizeO][N]                                       */
+int ofhe_scale_round_create(ofhe_ring* ring, uint32_t sizeI, const uint32_t* in_idx_h, uint32_t sizeO,
+                            const uint32_t* out_idx_h, int out_limbs_first, const uint64_t* tbl_h, const double* frac_h,
+                            ofhe_bconv** out);
+int ofhe_bconv_apply(ofhe_bconv* t, const uint64_t* in_d, uint64_t* out_d, void* stream);
+void ofhe_bconv_destroy(ofhe_bconv* t);
+
 /* ---- hybrid key switching.  The ring must hold Q at indices [0,sizeQ) and P at [sizeQ, sizeQ+sizeP).
  *      Tables: CryptoParametersRNS::PrecomputeCRTTables      pke/lib/schemerns/rns-cryptoparameters.cpp:48-401
  *              CryptoParametersCKKSRNS::PrecomputeCRTTables  pke/lib/scheme/ckksrns/ckksrns-cryptoparameters.cpp:44-160 */

@@ -35,7 +35,26 @@ struct BConvDev {
     uint32_t sizeQ, sizeP;
     const uint64_t* qhatinv;  // [sizeQ][2]  (w, Shoup(w))
     const uint2* mat;         // [sizeQ][sizeP]  (lo30, hi30)
+    int mode;                 // 0 approx (a10), 1 exact (a12), 2 scale-and-round (a13)
+    const double* dbl;        // [sizeQ]  qInv (mode 1) / tOSHatInvModsDivsFrac (mode 2)
+    const uint64_t* alpha;    // [sizeQ+1][sizeP]  alphaQModp (mode 1)
+    const uint64_t* extra;    // [sizeP]  tOSHatInvModsDivsModo[j][sizeI] (mode 2)
 };
+
+// (unsigned __int128) of a double above 2^63 (the reference's static_cast<DoubleNativeInt>(nu), dcrtpoly-impl.h:1569)
+__device__ __forceinline__ void double_to_u128(double d, uint64_t& hi, uint64_t& lo) {
+    const uint64_t bits = (uint64_t)__double_as_longlong(d);
+    const uint64_t mant = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+    const int sh        = (int)((bits >> 52) & 0x7ff) - 1075;  // value = mant * 2^sh, sh in [11, 75) here
+    if (sh >= 64) {
+        hi = mant << (sh - 64);
+        lo = 0;
+    }
+    else {
+        hi = sh ? mant >> (64 - sh) : 0;
+        lo = mant << sh;
+    }
+}
 
 __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
     uint64_t d;
@@ -48,8 +67,9 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
 // matrix read from shared memory then feeds 16 IMADs)
 template <int CH, int kCPT>
 __global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, LimbMap qmap, LimbMap pmap,
-                                                          const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
-                                                          size_t in_stride, size_t out_stride, int premultiplied) {
+                                                          PosMap xomap, const uint64_t* __restrict__ in,
+                                                          uint64_t* __restrict__ out, size_t in_stride,
+                                                          size_t out_stride, int premultiplied) {
     constexpr int MAXQ = 16 * CH;
     __shared__ __align__(16) uint2 s_mat[MAXQ * kJPT];
     __shared__ uint64_t s_src[MAXQ * 3];  // q, w, ws
@@ -78,16 +98,21 @@ __global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, 
     const uint32_t N   = r.N;
     const uint32_t rr0 = blockIdx.x * (kThreads * kCPT) + threadIdx.x;  // coefficient c of this thread: rr0 + c*kThreads
     uint32_t y0[kCPT][MAXQ], y1[kCPT][MAXQ];
+    double nu[kCPT];  // modes 1, 2: the floating-point overflow / rounding estimate, accumulated in index order with
+                      // separately rounded multiply and add (no FMA contraction), exactly as the reference's loop
 #pragma unroll
     for (int c = 0; c < kCPT; ++c) {
         const uint32_t rr = min(rr0 + c * kThreads, N - 1);  // clamped (branch-free); stores are predicated below
+        nu[c]             = 0.5;
 #pragma unroll
         for (int i = 0; i < MAXQ; ++i) {
             const int ii = i < (int)t.sizeQ ? i : 0;  // padded rows re-read row 0 and are zeroed
             uint64_t y   = in[(size_t)qmap.pos[ii] * N + rr];
-            if (!premultiplied)
+            if (!premultiplied && t.mode != 2)
                 y = shoup(y, s_src[3 * ii + 1], s_src[3 * ii + 2], s_src[3 * ii]);
             y        = i < (int)t.sizeQ ? y : 0;
+            if (t.mode != 0 && i < (int)t.sizeQ)
+                nu[c] = __dadd_rn(nu[c], __dmul_rn(__ull2double_rn(y), t.dbl[i]));
             y0[c][i] = (uint32_t)y & kMask30;
             y1[c][i] = (uint32_t)(y >> 30);
         }
@@ -144,8 +169,30 @@ __global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, 
 #pragma unroll
             for (int c = 0; c < kCPT; ++c) {
                 const uint32_t rr = rr0 + c * kThreads;
-                if (j0 + j + o < t.sizeP && rr < N)
-                    out[(size_t)pmap.pos[j0 + j + o] * N + rr] = csub(lazy_reduce_n(total[c][o], d[5], 0 - d[0]), d[0]);
+                if (j0 + j + o < t.sizeP && rr < N) {
+                    const uint32_t jj = j0 + j + o;
+                    const uint64_t p  = d[0];
+                    uint64_t v        = csub(lazy_reduce_n(total[c][o], d[5], 0 - p), p);
+                    if (t.mode == 1) {  // dcrtpoly-impl.h:1060,1073: minus alphaQModp[(size_t)nu][j]
+                        const uint64_t a = t.alpha[(size_t)__double2ull_rz(nu[c]) * t.sizeP + jj];
+                        v                = submod(v, a, p);
+                    }
+                    else if (t.mode == 2) {  // dcrtpoly-impl.h:1550-1586
+                        const ModConst mc = r.mc[pmap.idx[jj]];
+                        const uint64_t xo = in[(size_t)xomap.pos[jj] * N + rr];
+                        v                 = addmod(v, mulmod(xo, t.extra[jj], mc), p);
+                        uint64_t a;
+                        if (fabs(nu[c]) <= 9223372036854774784.0)  // isConvertableToNativeInt (utils/utilities.h:100-126)
+                            a = csub(lazy_reduce_n(__double2ull_rz(nu[c]), d[5], 0 - p), p);
+                        else {
+                            uint64_t hi, lo;
+                            double_to_u128(nu[c], hi, lo);
+                            a = barrett128(hi, lo, p, mc.mu128_hi, mc.mu128_lo);
+                        }
+                        v = addmod(v, a, p);
+                    }
+                    out[(size_t)pmap.pos[jj] * N + rr] = v;
+                }
             }
         }
     }
@@ -154,10 +201,9 @@ __global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, 
 }  // namespace
 
 BConv::~BConv() {
-    if (qhatinv_d)
-        cudaFree(qhatinv_d);
-    if (mat_d)
-        cudaFree(mat_d);
+    for (void* p : {(void*)qhatinv_d, (void*)mat_d, (void*)dbl_d, (void*)alpha_d, (void*)extra_d})
+        if (p)
+            cudaFree(p);
 }
 
 void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* out, uint32_t batch, size_t in_stride,
@@ -165,7 +211,7 @@ void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* o
     if (t.sizeP == 0 || t.sizeQ == 0 || batch == 0)
         return;
     OFHE_REQUIRE(t.sizeQ <= 64, "base conversion supports at most 64 source limbs");
-    BConvDev d{t.sizeQ, t.sizeP, t.qhatinv_d, reinterpret_cast<const uint2*>(t.mat_d)};
+    BConvDev d{t.sizeQ, t.sizeP, t.qhatinv_d, reinterpret_cast<const uint2*>(t.mat_d), t.mode, t.dbl_d, t.alpha_d, t.extra_d};
     static const int cpt1 = [] {
         const char* e = getenv("OFHE_BCONV_CPT");  // tuning knob: coefficients per thread for <= 16 source limbs
         return e ? atoi(e) : 1;
@@ -174,15 +220,15 @@ void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* o
     dim3 grid((r.N + kThreads * cpt - 1) / (kThreads * cpt), (t.sizeP + kJPT - 1) / kJPT, batch);
     const int pm = premultiplied ? 1 : 0;
     if (t.sizeQ <= 16 && cpt == 2)
-        bconv_kernel<1, 2><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+        bconv_kernel<1, 2><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
     else if (t.sizeQ <= 16)
-        bconv_kernel<1, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+        bconv_kernel<1, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
     else if (t.sizeQ <= 32)
-        bconv_kernel<2, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+        bconv_kernel<2, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
     else if (t.sizeQ <= 48)
-        bconv_kernel<3, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+        bconv_kernel<3, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
     else
-        bconv_kernel<4, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, in, out, in_stride, out_stride, pm);
+        bconv_kernel<4, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
     OFHE_CUDA(cudaGetLastError());
 }
 

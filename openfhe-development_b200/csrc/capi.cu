@@ -30,6 +30,10 @@ struct ofhe_evk {
 struct ofhe_shard {
     Shard* s;
 };
+struct ofhe_bconv {
+    std::unique_ptr<BConv> t;
+    Ring* r;
+};
 
 namespace {
 thread_local std::string g_err;
@@ -269,6 +273,95 @@ int ofhe_approx_switch_crt_basis(ofhe_ring* ring, uint32_t n_src, const uint32_t
         }
         launch_bconv(*ring->r, *t, in_d, out_d, 1, 0, 0, /*premultiplied=*/false, S(stream));
     });
+}
+
+static void upload(void** dptr, const void* h, size_t bytes) {
+    OFHE_CUDA(cudaMalloc(dptr, bytes));
+    OFHE_CUDA(cudaMemcpy(*dptr, h, bytes, cudaMemcpyHostToDevice));
+}
+static std::unique_ptr<BConv> bconv_from_tables(const Ring& r, uint32_t n_src, const uint32_t* src, const uint32_t* src_pos,
+                                                const uint64_t* hatinv, uint32_t n_dst, const uint32_t* dst,
+                                                const uint64_t* mat_h, bool dst_major, uint32_t mat_cols) {
+    OFHE_REQUIRE(n_src >= 1 && n_src <= 64 && n_dst >= 1 && n_dst <= (uint32_t)kMaxLimbs, "base conversion: unsupported basis size");
+    std::vector<uint64_t> hinv(2 * (size_t)n_src);
+    std::vector<uint32_t> mat(2 * (size_t)n_src * n_dst);
+    for (uint32_t i = 0; i < n_src; ++i) {
+        const uint64_t q = r.moduli[src[i]];
+        hinv[2 * i]      = hatinv ? hatinv[i] % q : 1;
+        hinv[2 * i + 1]  = hm::shoup_const(hinv[2 * i], q);
+        for (uint32_t j = 0; j < n_dst; ++j) {
+            const uint64_t m = (dst_major ? mat_h[(size_t)j * mat_cols + i] : mat_h[(size_t)i * mat_cols + j]);
+            OFHE_REQUIRE(m < (uint64_t(1) << 60), "base conversion: table entries must be below 2^60");
+            mat[2 * ((size_t)i * n_dst + j)]     = (uint32_t)(m & ((1u << 30) - 1));
+            mat[2 * ((size_t)i * n_dst + j) + 1] = (uint32_t)(m >> 30);
+        }
+    }
+    auto t   = std::make_unique<BConv>();
+    t->sizeQ = n_src;
+    t->sizeP = n_dst;
+    t->qmap  = make_map(src, n_src);
+    if (src_pos)
+        for (uint32_t i = 0; i < n_src; ++i)
+            t->qmap.pos[i] = (uint16_t)src_pos[i];
+    t->pmap = make_map(dst, n_dst);
+    upload((void**)&t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size());
+    upload((void**)&t->mat_d, mat.data(), sizeof(uint32_t) * mat.size());
+    return t;
+}
+
+int ofhe_bconv_create(ofhe_ring* ring, uint32_t n_src, const uint32_t* src_idx_h, const uint64_t* QHatInvModq_h,
+                      uint32_t n_dst, const uint32_t* dst_idx_h, const uint64_t* QHatModp_h, int table_is_dst_major,
+                      const uint64_t* alphaQModp_h, const double* qInv_h, ofhe_bconv** out) {
+    return guard([&] {
+        OFHE_REQUIRE(ring && src_idx_h && dst_idx_h && QHatInvModq_h && QHatModp_h && out, "null argument");
+        OFHE_REQUIRE((alphaQModp_h == nullptr) == (qInv_h == nullptr), "alphaQModp and qInv must be given together");
+        Ring* r = ring->r;
+        use(r);
+        checked_map(r, n_src, src_idx_h);
+        checked_map(r, n_dst, dst_idx_h);
+        auto t = bconv_from_tables(*r, n_src, src_idx_h, nullptr, QHatInvModq_h, n_dst, dst_idx_h, QHatModp_h,
+                                   table_is_dst_major != 0, table_is_dst_major ? n_src : n_dst);
+        if (alphaQModp_h) {
+            t->mode = 1;
+            upload((void**)&t->dbl_d, qInv_h, sizeof(double) * n_src);
+            upload((void**)&t->alpha_d, alphaQModp_h, sizeof(uint64_t) * (size_t)(n_src + 1) * n_dst);
+        }
+        *out = new ofhe_bconv{std::move(t), r};
+    });
+}
+int ofhe_scale_round_create(ofhe_ring* ring, uint32_t sizeI, const uint32_t* in_idx_h, uint32_t sizeO,
+                            const uint32_t* out_idx_h, int out_limbs_first, const uint64_t* tbl_h, const double* frac_h,
+                            ofhe_bconv** out) {
+    return guard([&] {
+        OFHE_REQUIRE(ring && in_idx_h && out_idx_h && tbl_h && frac_h && out, "null argument");
+        Ring* r = ring->r;
+        use(r);
+        checked_map(r, sizeI, in_idx_h);
+        checked_map(r, sizeO, out_idx_h);
+        const uint32_t inputIndex = out_limbs_first ? sizeO : 0, outputIndex = out_limbs_first ? 0 : sizeI;
+        std::vector<uint32_t> src_pos(sizeI);
+        for (uint32_t i = 0; i < sizeI; ++i)
+            src_pos[i] = inputIndex + i;  // dcrtpoly-impl.h:1527-1534
+        auto t  = bconv_from_tables(*r, sizeI, in_idx_h, src_pos.data(), nullptr, sizeO, out_idx_h, tbl_h, true, sizeI + 1);
+        t->mode = 2;
+        std::vector<uint64_t> extra(sizeO);
+        for (uint32_t j = 0; j < sizeO; ++j) {
+            extra[j]          = tbl_h[(size_t)j * (sizeI + 1) + sizeI];
+            t->xomap.pos[j]   = (uint16_t)(outputIndex + j);
+        }
+        upload((void**)&t->dbl_d, frac_h, sizeof(double) * sizeI);
+        upload((void**)&t->extra_d, extra.data(), sizeof(uint64_t) * sizeO);
+        *out = new ofhe_bconv{std::move(t), r};
+    });
+}
+int ofhe_bconv_apply(ofhe_bconv* t, const uint64_t* in_d, uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(t->r);
+        launch_bconv(*t->r, *t->t, in_d, out_d, 1, 0, 0, /*premultiplied=*/false, S(stream));
+    });
+}
+void ofhe_bconv_destroy(ofhe_bconv* t) {
+    delete t;
 }
 
 // ------------------------------------------------------------------------------------------------ hybrid key switch

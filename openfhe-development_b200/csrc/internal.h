@@ -136,6 +136,14 @@ struct BConv {
     // device: per source limb QHatInvModq + Shoup constant; matrix QHatModp split in 30-bit halves [sizeQ][sizeP]
     uint64_t* qhatinv_d = nullptr;   // [sizeQ][2] (w, ws)
     uint32_t* mat_d = nullptr;       // [sizeQ][sizeP][2] (lo30, hi30)
+    // mode 0: ApproxSwitchCRTBasis (a10).  mode 1: exact SwitchCRTBasis (a12): nu = 0.5 + sum double(y_i)*dbl[i],
+    // subtract alpha_d[(size_t)nu][j].  mode 2: ScaleAndRound (a13): sources are used as they are, nu = 0.5 +
+    // sum dbl[i]*double(x_i) is ADDED (mod o_j) together with x_{o_j} * extra_d[j]; xomap.pos[j] = row of x_{o_j} in `in`.
+    int mode = 0;
+    double* dbl_d = nullptr;         // [sizeQ]
+    uint64_t* alpha_d = nullptr;     // [sizeQ+1][sizeP]
+    uint64_t* extra_d = nullptr;     // [sizeP]
+    PosMap xomap;
     ~BConv();
 };
 // `batch` independent polynomials, `in_stride` / `out_stride` words apart

@@ -42,6 +42,10 @@ SIGNATURES = {
     "ofhe_automorphism": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "ofhe_automorphism_map_host": (C.c_int, [_vp, C.c_uint32, _vp]),
     "ofhe_approx_switch_crt_basis": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_bconv_create": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp, C.c_int, _vp, _vp, C.POINTER(_vp)]),
+    "ofhe_scale_round_create": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, C.c_int, _vp, _vp, C.POINTER(_vp)]),
+    "ofhe_bconv_apply": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "ofhe_bconv_destroy": (None, [_vp]),
     "ofhe_hks_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
     "ofhe_hks_destroy": (None, [_vp]),
     "ofhe_hks_num_per_part": (C.c_uint32, [_vp]),
@@ -250,6 +254,44 @@ class Ring:
     def fill_uniform(self, dst, mod_idx, seed):
         mi = _idx(mod_idx)
         _ck(lib().ofhe_fill_uniform(self.h, _ptr(dst), len(mi), mi.ctypes.data, seed, _stream()))
+
+
+class BaseConv:
+    """Table-driven base conversion (a10 with explicit tables, a12 exact SwitchCRTBasis, a13 ScaleAndRound)."""
+
+    def __init__(self, h):
+        self.h = h
+
+    @classmethod
+    def switch_crt_basis(cls, ring, src_idx, QHatInvModq, dst_idx, QHatModp, dst_major, alphaQModp=None, qInv=None):
+        si, di = _idx(src_idx), _idx(dst_idx)
+        hi = np.ascontiguousarray(QHatInvModq, dtype=np.uint64)
+        m = np.ascontiguousarray(QHatModp, dtype=np.uint64)
+        a = None if alphaQModp is None else np.ascontiguousarray(alphaQModp, dtype=np.uint64)
+        d = None if qInv is None else np.ascontiguousarray(qInv, dtype=np.float64)
+        h = _vp()
+        _ck(lib().ofhe_bconv_create(ring.h, len(si), si.ctypes.data, hi.ctypes.data, len(di), di.ctypes.data,
+                                    m.ctypes.data, int(dst_major), None if a is None else a.ctypes.data,
+                                    None if d is None else d.ctypes.data, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def scale_and_round(cls, ring, in_idx, out_idx, out_limbs_first, tbl, frac):
+        ii, oi = _idx(in_idx), _idx(out_idx)
+        t = np.ascontiguousarray(tbl, dtype=np.uint64)
+        f = np.ascontiguousarray(frac, dtype=np.float64)
+        h = _vp()
+        _ck(lib().ofhe_scale_round_create(ring.h, len(ii), ii.ctypes.data, len(oi), oi.ctypes.data,
+                                          int(out_limbs_first), t.ctypes.data, f.ctypes.data, C.byref(h)))
+        return cls(h)
+
+    def apply(self, src, dst):
+        _ck(lib().ofhe_bconv_apply(self.h, _ptr(src), _ptr(dst), _stream()))
+
+    def close(self):
+        if self.h:
+            lib().ofhe_bconv_destroy(self.h)
+            self.h = None
 
 
 class EvalKey:

@@ -834,3 +834,85 @@ void orc_ckks_automorphism_ct(const orc_ckks* c, uint32_t sizeQl, uint32_t k, co
     }
     free(ab), free(map);
 }
+
+
+/* ------------------------------------------------------------------ a12: exact SwitchCRTBasis (BFV, HPS)
+ * dcrtpoly-impl.h:1046-1084: as a10 plus the overflow count  nu = 0.5 + sum_i double(y_i) * qInv[i]  (IEEE double,
+ * one multiply then one add per term, in index order, NO fused multiply-add), alpha = (size_t)nu, and
+ * out_j = ( Barrett128(sum_i y_i * QHatModp[j][i]) - alphaQModp[alpha][j] ) mod p_j.   NOTE the [j][i] table order. */
+void orc_switch_crt_basis(uint32_t N, uint32_t sizeQ, const uint64_t* q, const uint64_t* QHatInvModq, uint32_t sizeP,
+                          const uint64_t* p, const uint64_t* QHatModp /*[sizeP][sizeQ]*/,
+                          const uint64_t* alphaQModp /*[sizeQ+1][sizeP]*/, const double* qInv, const uint64_t* in,
+                          uint64_t* out) {
+    uint64_t* pre = (uint64_t*)malloc(sizeof(uint64_t) * (sizeQ + 2 * sizeP));
+    uint64_t *muh = pre + sizeQ, *mul = muh + sizeP;
+    for (uint32_t i = 0; i < sizeQ; ++i)
+        pre[i] = orc_shoup_precon(QHatInvModq[i], q[i]);
+    for (uint32_t j = 0; j < sizeP; ++j)
+        orc_barrett128_mu(p[j], &muh[j], &mul[j]);
+#pragma omp parallel
+    {
+        uint64_t* y = (uint64_t*)malloc(sizeof(uint64_t) * sizeQ);
+#pragma omp for
+        for (uint32_t r = 0; r < N; ++r) {
+            volatile double nu = 0.5; /* volatile: keep every intermediate rounded to double */
+            for (uint32_t i = 0; i < sizeQ; ++i) {
+                y[i]              = orc_mulmod_shoup(in[(size_t)i * N + r], QHatInvModq[i], pre[i], q[i]);
+                volatile double t = (double)y[i] * qInv[i];
+                nu                = nu + t;
+            }
+            size_t alpha = (size_t)nu;
+            for (uint32_t j = 0; j < sizeP; ++j) {
+                u128 sum = 0;
+                for (uint32_t i = 0; i < sizeQ; ++i)
+                    sum += (u128)y[i] * QHatModp[(size_t)j * sizeQ + i];
+                uint64_t v = orc_barrett128((uint64_t)(sum >> 64), (uint64_t)sum, p[j], muh[j], mul[j]);
+                uint64_t a = alphaQModp[alpha * sizeP + j];
+                out[(size_t)j * N + r] = v >= a ? v - a : v + p[j] - a; /* ModSubFast */
+            }
+        }
+        free(y);
+    }
+    free(pre);
+}
+
+/* ------------------------------------------------------------------ a13: ScaleAndRound DCRT -> DCRT (BFV)
+ * dcrtpoly-impl.h:1513-1586.  in: [sizeI + sizeO][N]; the sizeO output-basis limbs are first when in_first == 0
+ * (output modulus == first input modulus: inputIndex = sizeO), else last (outputIndex = sizeI).
+ * nu = 0.5 + sum_i frac[i] * double(x_i);  if nu <= 2^63 - 1024 (isConvertableToNativeInt, utils/utilities.h:100-126)
+ * alpha = (uint64)nu reduced mod o_j, else alpha = (uint128)nu reduced by Barrett128;
+ * out_j = Barrett128( sum_i x_i * tbl[j][i] + x_{o_j} * tbl[j][sizeI] ) + alpha  (mod o_j).                         */
+void orc_scale_and_round(uint32_t N, uint32_t sizeI, uint32_t sizeO, const uint64_t* o, int out_limbs_first,
+                         const uint64_t* tbl /*[sizeO][sizeI+1]*/, const double* frac, const uint64_t* in,
+                         uint64_t* out) {
+    uint32_t inputIndex = out_limbs_first ? sizeO : 0, outputIndex = out_limbs_first ? 0 : sizeI;
+    uint64_t* muh = (uint64_t*)malloc(sizeof(uint64_t) * 2 * sizeO);
+    uint64_t* mul = muh + sizeO;
+    for (uint32_t j = 0; j < sizeO; ++j)
+        orc_barrett128_mu(o[j], &muh[j], &mul[j]);
+    const double limit = 9223372036854774784.0; /* (double)(2^63 - 2^9 - 1) */
+#pragma omp parallel for
+    for (uint32_t r = 0; r < N; ++r) {
+        volatile double nu = 0.5;
+        for (uint32_t i = 0; i < sizeI; ++i) {
+            volatile double t = frac[i] * (double)in[(size_t)(i + inputIndex) * N + r];
+            nu                = nu + t;
+        }
+        int small        = fabs(nu) <= limit;
+        uint64_t alpha64 = small ? (uint64_t)nu : 0;
+        u128 alpha128    = small ? 0 : (u128)nu;
+        for (uint32_t j = 0; j < sizeO; ++j) {
+            const uint64_t* tj = tbl + (size_t)j * (sizeI + 1);
+            u128 sum           = 0;
+            for (uint32_t i = 0; i < sizeI; ++i)
+                sum += (u128)in[(size_t)(i + inputIndex) * N + r] * tj[i];
+            sum += (u128)in[(size_t)(outputIndex + j) * N + r] * tj[sizeI];
+            uint64_t v = orc_barrett128((uint64_t)(sum >> 64), (uint64_t)sum, o[j], muh[j], mul[j]);
+            uint64_t a = small ? (alpha64 >= o[j] ? alpha64 % o[j] : alpha64)
+                               : orc_barrett128((uint64_t)(alpha128 >> 64), (uint64_t)alpha128, o[j], muh[j], mul[j]);
+            uint64_t s = v + a;
+            out[(size_t)j * N + r] = s >= o[j] ? s - o[j] : s;
+        }
+    }
+    free(muh);
+}

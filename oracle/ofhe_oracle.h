@@ -51,6 +51,13 @@ void orc_approx_switch_crt_basis(uint32_t N, uint32_t sizeQ, const uint64_t* q, 
                                  uint32_t sizeP, const uint64_t* p, const uint64_t* QHatModp, const uint64_t* in,
                                  uint64_t* out);
 
+/* a12 exact base conversion (QHatModp is [sizeP][sizeQ], alphaQModp [sizeQ+1][sizeP]) and a13 scale-and-round */
+void orc_switch_crt_basis(uint32_t N, uint32_t sizeQ, const uint64_t* q, const uint64_t* QHatInvModq, uint32_t sizeP,
+                          const uint64_t* p, const uint64_t* QHatModp, const uint64_t* alphaQModp, const double* qInv,
+                          const uint64_t* in, uint64_t* out);
+void orc_scale_and_round(uint32_t N, uint32_t sizeI, uint32_t sizeO, const uint64_t* o, int out_limbs_first,
+                         const uint64_t* tbl, const double* frac, const uint64_t* in, uint64_t* out);
+
 /* a20 CKKS / HYBRID tables */
 typedef struct orc_ckks orc_ckks;
 /* scal_tech: 0 FIXEDMANUAL, 1 FIXEDAUTO, 2 FLEXIBLEAUTO (FLEXIBLEAUTOEXT not restated) */

@@ -606,4 +606,202 @@ int ref_ckks_decrypt(void* hv, uint32_t sizeQl, uint32_t deg, const uint64_t* ct
     });
 }
 
+
+// ---------------------------------------------------------------- BFV (HPSPOVERQ) context: rows a12 / a13 (config 3)
+struct BfvCtx {
+    CryptoContext<DCRTPoly> cc;
+    KeyPair<DCRTPoly> keys;
+    std::shared_ptr<CryptoParametersBFVRNS> cp;
+    Ciphertext<DCRTPoly> tmpl;
+    uint32_t N, sizeQ, sizeR;
+};
+static void dump_mat(const std::vector<std::vector<NativeInteger>>& m, uint64_t* out) {  // row-major as stored
+    size_t k = 0;
+    for (auto& row : m)
+        for (auto& v : row)
+            out[k++] = v.ConvertToInt<uint64_t>();
+}
+void* ref_bfv_create(uint32_t ring_dim, uint32_t depth, uint32_t scale_bits, uint64_t ptm, uint32_t dnum) {
+    BfvCtx* h = nullptr;
+    int rc    = guarded([&] {
+        CCParams<CryptoContextBFVRNS> p;
+        p.SetRingDim(ring_dim);
+        p.SetPlaintextModulus(ptm);
+        p.SetMultiplicativeDepth(depth);
+        p.SetScalingModSize(scale_bits);
+        p.SetMultiplicationTechnique(HPSPOVERQ);
+        p.SetKeySwitchTechnique(HYBRID);
+        p.SetSecurityLevel(HEStd_NotSet);
+        if (dnum)
+            p.SetNumLargeDigits(dnum);
+        auto cc = GenCryptoContext(p);
+        cc->Enable(PKE);
+        cc->Enable(KEYSWITCH);
+        cc->Enable(LEVELEDSHE);
+        h       = new BfvCtx();
+        h->cc   = cc;
+        h->keys = cc->KeyGen();
+        cc->EvalMultKeyGen(h->keys.secretKey);
+        h->cp    = std::dynamic_pointer_cast<CryptoParametersBFVRNS>(cc->GetCryptoParameters());
+        h->N     = cc->GetRingDimension();
+        h->sizeQ = h->cp->GetElementParams()->GetParams().size();
+        h->sizeR = h->cp->GetParamsRl(h->sizeQ - 1)->GetParams().size();
+        std::vector<int64_t> msg{1, 2, 3, 4};
+        h->tmpl = cc->Encrypt(h->keys.publicKey, cc->MakePackedPlaintext(msg));
+    });
+    return rc == 0 ? h : nullptr;
+}
+void ref_bfv_destroy(void* hv) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    if (h) {
+        h->cc->ClearEvalMultKeys();
+        delete h;
+    }
+}
+// shape: N, sizeQ, sizeR;  moduli/roots: Q then R (the auxiliary basis of HPSPOVERQ at full level)
+void ref_bfv_shape(void* hv, uint32_t* shape, uint64_t* moduli, uint64_t* roots) {
+    auto* h  = static_cast<BfvCtx*>(hv);
+    shape[0] = h->N;
+    shape[1] = h->sizeQ;
+    shape[2] = h->sizeR;
+    if (moduli) {
+        const auto& ps = h->cp->GetParamsQlRl(h->sizeQ - 1)->GetParams();
+        for (size_t i = 0; i < ps.size(); ++i) {
+            moduli[i] = ps[i]->GetModulus().ConvertToInt<uint64_t>();
+            roots[i]  = ps[i]->GetRootOfUnity().ConvertToInt<uint64_t>();
+        }
+    }
+}
+// tables of the full-level EvalMult (bfvrns-leveledshe.cpp:239-261,385-396), l = sizeQ-1
+//  which: 0 QlHatInvModq[sizeQ]  1 QlHatModr[sizeR][sizeQ]  2 alphaQlModr[sizeQ+1][sizeR]  3 qInv (double)[sizeQ]
+//         4 mNegRlQlHatInvModq[sizeQ]  5 qInvModr[sizeQ][sizeR]  6 RlHatInvModr[sizeR]  7 RlHatModq[sizeQ][sizeR]
+//         8 alphaRlModq[sizeR+1][sizeQ]  9 rInv (double)[sizeR]  10 tQlSlHatInvModsDivsModq[sizeQ][sizeR+1]
+//         11 tQlSlHatInvModsDivsFrac (double)[sizeR]
+int ref_bfv_table(void* hv, int which, void* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto cp       = h->cp;
+        uint32_t l    = h->sizeQ - 1;
+        uint64_t* u   = static_cast<uint64_t*>(out);
+        double* d     = static_cast<double*>(out);
+        auto dump_dbl = [&](const std::vector<double>& v) { std::copy(v.begin(), v.end(), d); };
+        switch (which) {
+            case 0: copy_vec(cp->GetQlHatInvModq(l), u); break;
+            case 1: dump_mat(cp->GetQlHatModr(l), u); break;
+            case 2: dump_mat(cp->GetalphaQlModr(l), u); break;
+            case 3: dump_dbl(cp->GetqInv()); break;
+            case 4: copy_vec(cp->GetmNegRlQlHatInvModq(l), u); break;
+            case 5: dump_mat(cp->GetqInvModr(), u); break;
+            case 6: copy_vec(cp->GetRlHatInvModr(l), u); break;
+            case 7: dump_mat(cp->GetRlHatModq(l), u); break;
+            case 8: dump_mat(cp->GetalphaRlModq(l), u); break;
+            case 9: dump_dbl(cp->GetrInv()); break;
+            case 10: dump_mat(cp->GettQlSlHatInvModsDivsModq(l), u); break;
+            case 11: dump_dbl(cp->GettQlSlHatInvModsDivsFrac(l)); break;
+            default: OPENFHE_THROW("unknown table");
+        }
+    });
+}
+// dimensions of table `which` as (rows, cols); cols == 0 for vectors
+void ref_bfv_table_dims(void* hv, int which, uint32_t* rows, uint32_t* cols) {
+    auto* h    = static_cast<BfvCtx*>(hv);
+    auto cp    = h->cp;
+    uint32_t l = h->sizeQ - 1;
+    auto md    = [&](const std::vector<std::vector<NativeInteger>>& m) { *rows = m.size(); *cols = m.empty() ? 0 : m[0].size(); };
+    *cols      = 0;
+    switch (which) {
+        case 0: *rows = cp->GetQlHatInvModq(l).size(); break;
+        case 1: md(cp->GetQlHatModr(l)); break;
+        case 2: md(cp->GetalphaQlModr(l)); break;
+        case 3: *rows = cp->GetqInv().size(); break;
+        case 4: *rows = cp->GetmNegRlQlHatInvModq(l).size(); break;
+        case 5: md(cp->GetqInvModr()); break;
+        case 6: *rows = cp->GetRlHatInvModr(l).size(); break;
+        case 7: md(cp->GetRlHatModq(l)); break;
+        case 8: md(cp->GetalphaRlModq(l)); break;
+        case 9: *rows = cp->GetrInv().size(); break;
+        case 10: md(cp->GettQlSlHatInvModsDivsModq(l)); break;
+        case 11: *rows = cp->GettQlSlHatInvModsDivsFrac(l).size(); break;
+        default: *rows = 0;
+    }
+}
+static std::shared_ptr<ILDCRTParams<BigInteger>> bfv_params(BfvCtx* h, int which /*0 Q, 1 R, 2 QR*/) {
+    uint32_t l = h->sizeQ - 1;
+    return which == 0 ? h->cp->GetParamsQl(l) : (which == 1 ? h->cp->GetParamsRl(l) : h->cp->GetParamsQlRl(l));
+}
+// ExpandCRTBasis Q -> QR (a12; exact SwitchCRTBasis inside): in [sizeQ][N] EVALUATION -> out [sizeQ+sizeR][N] EVALUATION
+int ref_bfv_expand_crt_basis(void* hv, const uint64_t* in, uint64_t* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto cp    = h->cp;
+        uint32_t l = h->sizeQ - 1;
+        DCRTPoly x = make_poly(bfv_params(h, 0), Format::EVALUATION, in);
+        x.ExpandCRTBasis(cp->GetParamsQlRl(l), cp->GetParamsRl(l), cp->GetQlHatInvModq(l), cp->GetQlHatInvModqPrecon(l),
+                         cp->GetQlHatModr(l), cp->GetalphaQlModr(l), cp->GetModrBarrettMu(), cp->GetqInv(),
+                         Format::EVALUATION);
+        dump_poly(x, out);
+    });
+}
+// SwitchCRTBasis Q -> R alone: in [sizeQ][N] COEFFICIENT -> out [sizeR][N] COEFFICIENT
+int ref_bfv_switch_crt_basis(void* hv, const uint64_t* in, uint64_t* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto cp    = h->cp;
+        uint32_t l = h->sizeQ - 1;
+        DCRTPoly x = make_poly(bfv_params(h, 0), Format::COEFFICIENT, in);
+        dump_poly(x.SwitchCRTBasis(cp->GetParamsRl(l), cp->GetQlHatInvModq(l), cp->GetQlHatInvModqPrecon(l),
+                                   cp->GetQlHatModr(l), cp->GetalphaQlModr(l), cp->GetModrBarrettMu(), cp->GetqInv()),
+                  out);
+    });
+}
+// FastExpandCRTBasisPloverQ: in [sizeQ][N] COEFFICIENT -> out [sizeQ+sizeR][N] COEFFICIENT (bfvrns-leveledshe.cpp:248-261)
+int ref_bfv_fast_expand_p_over_q(void* hv, const uint64_t* in, uint64_t* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto cp    = h->cp;
+        uint32_t l = h->sizeQ - 1;
+        DCRTPoly::CRTBasisExtensionPrecomputations basisPQ(
+            cp->GetParamsQlRl(l), cp->GetParamsRl(l), cp->GetParamsQl(l), cp->GetmNegRlQlHatInvModq(l),
+            cp->GetmNegRlQlHatInvModqPrecon(l), cp->GetqInvModr(), cp->GetModrBarrettMu(), cp->GetRlHatInvModr(l),
+            cp->GetRlHatInvModrPrecon(l), cp->GetRlHatModq(l), cp->GetalphaRlModq(l), cp->GetModqBarrettMu(), cp->GetrInv());
+        DCRTPoly x = make_poly(bfv_params(h, 0), Format::COEFFICIENT, in);
+        x.FastExpandCRTBasisPloverQ(basisPQ);
+        dump_poly(x, out);
+    });
+}
+// ScaleAndRound QR -> Q by t/R (a13): in [sizeQ+sizeR][N] COEFFICIENT -> out [sizeQ][N] COEFFICIENT
+int ref_bfv_scale_and_round(void* hv, const uint64_t* in, uint64_t* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto cp    = h->cp;
+        uint32_t l = h->sizeQ - 1;
+        DCRTPoly x = make_poly(bfv_params(h, 2), Format::COEFFICIENT, in);
+        dump_poly(x.ScaleAndRound(cp->GetParamsQl(l), cp->GettQlSlHatInvModsDivsModq(l), cp->GettQlSlHatInvModsDivsFrac(l),
+                                  cp->GetModqBarrettMu()),
+                  out);
+    });
+}
+// cc->EvalMultNoRelin on caller-supplied towers: ct* = 2 polys [sizeQ][N] EVALUATION -> out = 3 polys [sizeQ][N] COEFFICIENT
+int ref_bfv_evalmult_norelin(void* hv, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto mk = [&](const uint64_t* d) {
+            auto ct = h->tmpl->Clone();
+            std::vector<DCRTPoly> el;
+            for (uint32_t k = 0; k < 2; ++k)
+                el.push_back(make_poly(bfv_params(h, 0), Format::EVALUATION, d + (size_t)k * h->sizeQ * h->N));
+            ct->SetElements(std::move(el));
+            return ct;
+        };
+        auto c = h->cc->EvalMultNoRelin(mk(ct1), mk(ct2));
+        if (c->GetElements().size() != 3)
+            OPENFHE_THROW("unexpected BFV EvalMult output shape");
+        for (uint32_t k = 0; k < 3; ++k) {
+            DCRTPoly e = c->GetElements()[k];
+            e.SetFormat(Format::COEFFICIENT);
+            dump_poly(e, out + (size_t)k * h->sizeQ * h->N);
+        }
+    });
+}
+
 }  // extern "C"

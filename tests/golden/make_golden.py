@@ -83,6 +83,32 @@ def main():
         g["dec_prod"] = c.decrypt(c.sizeQ, 2, prod, 4)
         np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **g)
         c.close()
+    # ---- BFV HPSPOVERQ (rows a12 / a13, config 3): a small context with every input / output, and the TABLES ONLY of
+    #      the config-3 shape (N = 2^15, 60-bit limbs, log2 q ~ 720 -> 12 Q limbs) for full-size oracle-vs-GPU tests
+    for tag, args, with_data in (("bfv_n64", (64, 2, 60, 65537, 0), True), ("bfv_n128_d4", (128, 4, 50, 786433, 0), True),
+                                 ("bfv_cfg3_tables", (1 << 15, 20, 60, 65537, 0), False)):
+        b = r.bfv(*args)
+        g = dict(args=np.array(args, dtype=np.int64), shape=np.array([b.N, b.sizeQ, b.sizeR]), moduli=b.moduli,
+                 roots=b.roots)
+        for k, v in b.tables().items():
+            g["T_" + k] = v
+        if with_data:
+            Q = b.moduli[:b.sizeQ]
+            xe, xc = seeded_residues(600, Q, b.N), seeded_residues(601, Q, b.N)
+            xq = seeded_residues(602, b.moduli, b.N)
+            # edge coefficients: zeros, q-1 everywhere, and a value making the overflow estimate land near an integer
+            xc[:, 0] = 0
+            xc[:, 1] = Q - np.uint64(1)
+            xq[:, 0] = 0
+            xq[:, 1] = b.moduli - np.uint64(1)
+            g.update(expand_in=xe, expand_out=b.expand_crt_basis(xe), switch_in=xc, switch_out=b.switch_crt_basis(xc),
+                     fastexp_in=xc, fastexp_out=b.fast_expand_p_over_q(xc), sr_in=xq, sr_out=b.scale_and_round(xq))
+            ct1 = np.stack([seeded_residues(603, Q, b.N), seeded_residues(604, Q, b.N)])
+            ct2 = np.stack([seeded_residues(605, Q, b.N), seeded_residues(606, Q, b.N)])
+            g.update(ct1=ct1, ct2=ct2, evalmult_norelin=b.evalmult_norelin(ct1, ct2))
+        print(tag, "sizeQ", b.sizeQ, "sizeR", b.sizeR)
+        np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **g)
+        b.close()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -88,6 +88,9 @@ class Oracle:
         _sig(L, "orc_automorphism_eval", None, C.c_uint32, u32p, u64p, u64p)
         _sig(L, "orc_approx_switch_crt_basis", None, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p,
              u64p, u64p)
+        _sig(L, "orc_switch_crt_basis", None, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p, u64p, f64p,
+             u64p, u64p)
+        _sig(L, "orc_scale_and_round", None, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_int, u64p, f64p, u64p, u64p)
         _sig(L, "orc_ckks_create", C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int)
         _sig(L, "orc_ckks_destroy", None, C.c_void_p)
         _sig(L, "orc_ckks_shape", None, C.c_void_p, u32p)
@@ -168,6 +171,23 @@ class Oracle:
         out = np.empty((len(p), x.shape[1]), dtype=np.uint64)
         self.L.orc_approx_switch_crt_basis(x.shape[1], len(q), q, np.ascontiguousarray(QHatInvModq), len(p), p,
                                            np.ascontiguousarray(QHatModp), np.ascontiguousarray(x), out)
+        return out
+
+    def switch_crt_basis(self, q, QHatInvModq, p, QHatModp_ji, alphaQModp, qInv, x):
+        """a12; QHatModp_ji is [sizeP][sizeQ] (the reference's order for this function)."""
+        q, p = np.ascontiguousarray(q, dtype=np.uint64), np.ascontiguousarray(p, dtype=np.uint64)
+        out = np.empty((len(p), x.shape[1]), dtype=np.uint64)
+        self.L.orc_switch_crt_basis(x.shape[1], len(q), q, np.ascontiguousarray(QHatInvModq), len(p), p,
+                                    np.ascontiguousarray(QHatModp_ji), np.ascontiguousarray(alphaQModp),
+                                    np.ascontiguousarray(qInv, dtype=np.float64), np.ascontiguousarray(x), out)
+        return out
+
+    def scale_and_round(self, o, out_limbs_first, tbl, frac, x):
+        o = np.ascontiguousarray(o, dtype=np.uint64)
+        sizeO, sizeI = len(o), x.shape[0] - len(o)
+        out = np.empty((sizeO, x.shape[1]), dtype=np.uint64)
+        self.L.orc_scale_and_round(x.shape[1], sizeI, sizeO, o, int(out_limbs_first), np.ascontiguousarray(tbl),
+                                   np.ascontiguousarray(frac, dtype=np.float64), np.ascontiguousarray(x), out)
         return out
 
     def ckks(self, N, depth, scale_bits, first_bits, dnum=0, scal_tech=0):
@@ -338,6 +358,15 @@ class Reference:
         _sig(L, "ref_ckks_time_evalmult", C.c_double, C.c_void_p, C.c_uint32, u64p, u64p, C.c_int, C.c_int)
         _sig(L, "ref_ckks_rescale", C.c_int, C.c_void_p, C.c_uint32, u64p, u64p)
         _sig(L, "ref_ckks_rotate", C.c_int, C.c_void_p, C.c_uint32, C.c_int32, u64p, u64p)
+        _sig(L, "ref_bfv_create", C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32)
+        _sig(L, "ref_bfv_destroy", None, C.c_void_p)
+        _sig(L, "ref_bfv_shape", None, C.c_void_p, u32p, C.c_void_p, C.c_void_p)
+        _sig(L, "ref_bfv_table", C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+        _sig(L, "ref_bfv_table_dims", None, C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32))
+        for n in ("ref_bfv_expand_crt_basis", "ref_bfv_switch_crt_basis", "ref_bfv_fast_expand_p_over_q",
+                  "ref_bfv_scale_and_round"):
+            _sig(L, n, C.c_int, C.c_void_p, u64p, u64p)
+        _sig(L, "ref_bfv_evalmult_norelin", C.c_int, C.c_void_p, u64p, u64p, u64p)
         _sig(L, "ref_ckks_encrypt", C.c_int, C.c_void_p, f64p, C.c_uint32, u64p)
         _sig(L, "ref_ckks_decrypt", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, u64p, f64p, C.c_uint32)
 
@@ -400,6 +429,9 @@ class Reference:
 
     def ckks(self, N, depth, scale_bits, first_bits, dnum=0, scal_tech=0):
         return ReferenceCkks(self, N, depth, scale_bits, first_bits, dnum, scal_tech)
+
+    def bfv(self, N, depth, scale_bits=60, ptm=65537, dnum=0):
+        return ReferenceBfv(self, N, depth, scale_bits, ptm, dnum)
 
 
 class ReferenceCkks(_CkksCommon):
@@ -533,4 +565,65 @@ class ReferenceCkks(_CkksCommon):
     def decrypt(self, sizeQl, deg, ct, n):
         out = np.empty(n, dtype=np.float64)
         self.r._ok(self.L.ref_ckks_decrypt(self.h, sizeQl, deg, np.ascontiguousarray(ct), out, n))
+        return out
+
+
+BFV_TABLES = {"QlHatInvModq": 0, "QlHatModr": 1, "alphaQlModr": 2, "qInv": 3, "mNegRlQlHatInvModq": 4, "qInvModr": 5,
+              "RlHatInvModr": 6, "RlHatModq": 7, "alphaRlModq": 8, "rInv": 9, "tQlSlHatInvModsDivsModq": 10,
+              "tQlSlHatInvModsDivsFrac": 11}
+_BFV_DOUBLE = {3, 9, 11}
+
+
+class ReferenceBfv:
+    """BFV (HPSPOVERQ) context of the unmodified reference: tables and DCRTPoly calls of rows a12 / a13."""
+
+    def __init__(self, ref, N, depth, scale_bits, ptm, dnum):
+        self.r, self.L = ref, ref.L
+        self.h = self.L.ref_bfv_create(N, depth, scale_bits, ptm, dnum)
+        if not self.h:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        s = np.zeros(3, dtype=np.uint32)
+        self.L.ref_bfv_shape(self.h, s, None, None)
+        self.N, self.sizeQ, self.sizeR = (int(v) for v in s)
+        self.moduli = np.empty(self.sizeQ + self.sizeR, dtype=np.uint64)
+        self.roots = np.empty_like(self.moduli)
+        self.L.ref_bfv_shape(self.h, s, self.moduli.ctypes.data, self.roots.ctypes.data)
+
+    def close(self):
+        if self.h:
+            self.L.ref_bfv_destroy(self.h)
+            self.h = None
+
+    def table(self, name):
+        w = BFV_TABLES[name]
+        rows, cols = C.c_uint32(), C.c_uint32()
+        self.L.ref_bfv_table_dims(self.h, w, C.byref(rows), C.byref(cols))
+        shape = (rows.value,) if cols.value == 0 else (rows.value, cols.value)
+        out = np.empty(shape, dtype=np.float64 if w in _BFV_DOUBLE else np.uint64)
+        self.r._ok(self.L.ref_bfv_table(self.h, w, out.ctypes.data))
+        return out
+
+    def tables(self):
+        return {k: self.table(k) for k in BFV_TABLES}
+
+    def _call(self, fn, x, n_out):
+        out = np.empty((n_out, self.N), dtype=np.uint64)
+        self.r._ok(getattr(self.L, fn)(self.h, np.ascontiguousarray(x), out))
+        return out
+
+    def expand_crt_basis(self, x):
+        return self._call("ref_bfv_expand_crt_basis", x, self.sizeQ + self.sizeR)
+
+    def switch_crt_basis(self, x):
+        return self._call("ref_bfv_switch_crt_basis", x, self.sizeR)
+
+    def fast_expand_p_over_q(self, x):
+        return self._call("ref_bfv_fast_expand_p_over_q", x, self.sizeQ + self.sizeR)
+
+    def scale_and_round(self, x):
+        return self._call("ref_bfv_scale_and_round", x, self.sizeQ)
+
+    def evalmult_norelin(self, ct1, ct2):
+        out = np.empty((3, self.sizeQ, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_bfv_evalmult_norelin(self.h, np.ascontiguousarray(ct1), np.ascontiguousarray(ct2), out))
         return out

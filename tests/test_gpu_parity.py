@@ -406,3 +406,40 @@ def test_config2_full_size(gpu, oracle):
             o.close()
     finally:
         c.close()
+
+
+def test_config4_shape_n17(gpu, oracle):
+    """BASELINE config 4 shape (simple-ckks-bootstrapping parameters at ring 2^17: depth 32 -> 33 + 11 limbs, dnum 3,
+    SURVEY.md Appendix B row 4a): the building blocks bootstrapping spends its time in -- EvalMult+relin, rescale and a
+    hoisted-style rotation -- at N = 2^17 (5-stage strided NTT kernels), full size, against the oracle."""
+    ctx, m = gpu
+    args = (1 << 17, 32, 59, 60, 0, 0)
+    p = m.ckks_paramgen(*args)
+    assert (p["sizeQ"], p["sizeP"], p["dnum"], p["alpha"]) == (33, 11, 3, 11)
+    N, sizeQ, sizeP, dnum = p["N"], p["sizeQ"], p["sizeP"], p["dnum"]
+    c = oracle.ckks(*args)
+    try:
+        assert (p["moduli"] == c.moduli).all() and (p["roots"] == c.roots).all()
+        ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+        hks = m.Hks(ring, sizeQ, sizeP, dnum)
+        ea = seeded_residues(91, np.tile(c.moduli, dnum), N).reshape(dnum, sizeQ + sizeP, N)
+        eb = seeded_residues(92, np.tile(c.moduli, dnum), N).reshape(dnum, sizeQ + sizeP, N)
+        evk = m.EvalKey(hks, ea, eb)
+        sizeQl = sizeQ
+        ct1 = np.stack([seeded_residues(93, c.moduli[:sizeQl], N), seeded_residues(94, c.moduli[:sizeQl], N)])
+        ct2 = np.stack([seeded_residues(95, c.moduli[:sizeQl], N), seeded_residues(96, c.moduli[:sizeQl], N)])
+        out = ctx.zeros(2, sizeQl, N)
+        hks.evalmult(sizeQl, ctx.upload(ct1), ctx.upload(ct2), evk, out)
+        want = c.evalmult(sizeQl, ct1, ct2, ea, eb)
+        assert (ctx.download(out) == want).all()
+        r = ctx.zeros(2, sizeQl - 1, N)
+        hks.rescale(sizeQl, out, r, 2)
+        assert (ctx.download(r)[1] == c.rescale_poly(sizeQl, want[1])).all()
+        k = m.find_automorphism_index(-5, 2 * N)
+        rot = ctx.zeros(2, sizeQl, N)
+        hks.rotate(sizeQl, k, ctx.upload(ct1), evk, rot)
+        assert (ctx.download(rot) == c.automorphism_ct(sizeQl, k, ct1, ea, eb)).all()
+        for o in (evk, hks, ring):
+            o.close()
+    finally:
+        c.close()
