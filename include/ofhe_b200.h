@@ -157,6 +157,12 @@ int ofhe_ckks_evalmult(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_d, co
 /*     same operation on HOST buffers: copies the inputs to the device, runs, copies the result back, synchronises.  */
 int ofhe_ckks_evalmult_host(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_h, const uint64_t* ct2_h,
                             const ofhe_evk* evk, uint64_t* out_h);
+/*     n independent multiplications on HOST buffers, software-pipelined: while multiplication k runs, the inputs of
+ *     k+1 stream in on the H2D copy engine and the result of k-1 streams out on the D2H engine (three staging slots,
+ *     one compute stream).  Host buffers must be page-locked for the copies to overlap.  ct1_h[i], ct2_h[i] and
+ *     out_h[i] are [2][sizeQl][N]; returns when every result is on the host.                                        */
+int ofhe_ckks_evalmult_host_batch(ofhe_hks* hks, uint32_t sizeQl, uint32_t n, const uint64_t* const* ct1_h,
+                                  const uint64_t* const* ct2_h, const ofhe_evk* evk, uint64_t* const* out_h);
 /* a14 DCRTPolyImpl::DropLastElementAndScale over n_polys polynomials (CKKS rescale)
  *     dcrtpoly-impl.h:693-712, pke/lib/scheme/ckksrns/ckksrns-leveledshe.cpp:172-191
  *     in_d [n_polys][sizeQl][N] -> out_d [n_polys][sizeQl-1][N]                                                     */

@@ -20,9 +20,12 @@ struct ofhe_ring {
 struct ofhe_hks {
     Hks* h;
     ofhe_ring* ring;
-    // pinned staging + device buffers of the *_host entry points (allocated on first use)
+    // device staging buffers of the *_host entry points (allocated on first use)
     uint64_t* stage_d = nullptr;
     size_t stage_words = 0;
+    // pipelined batch entry point: copy streams + per-slot events
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_in[3] = {}, ev_comp[3] = {}, ev_out[3] = {};
 };
 struct ofhe_evk {
     EvalKey* k;
@@ -385,6 +388,13 @@ void ofhe_hks_destroy(ofhe_hks* hks) {
     if (hks) {
         if (hks->stage_d)
             cudaFree(hks->stage_d);
+        for (cudaStream_t st : {hks->s_h2d, hks->s_d2h, hks->s_comp})
+            if (st)
+                cudaStreamDestroy(st);
+        for (int i = 0; i < 3; ++i)
+            for (cudaEvent_t e : {hks->ev_in[i], hks->ev_comp[i], hks->ev_out[i]})
+                if (e)
+                    cudaEventDestroy(e);
         delete hks->h;
         delete hks;
     }
@@ -577,6 +587,54 @@ int ofhe_ckks_evalmult_host(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* ct1_
         h.evalmult(sizeQl, d1, d2, *evk->k, d3, st);
         OFHE_CUDA(cudaMemcpyAsync(out_h, d3, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         OFHE_CUDA(cudaStreamSynchronize(st));
+    });
+}
+int ofhe_ckks_evalmult_host_batch(ofhe_hks* hks, uint32_t sizeQl, uint32_t n, const uint64_t* const* ct1_h,
+                                  const uint64_t* const* ct2_h, const ofhe_evk* evk, uint64_t* const* out_h) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        constexpr int S_   = 3;
+        const size_t words = 2 * (size_t)sizeQl * h.ring->N, bytes = words * sizeof(uint64_t);
+        if (hks->stage_words < 3 * S_ * words) {
+            if (hks->stage_d) {
+                OFHE_CUDA(cudaDeviceSynchronize());
+                OFHE_CUDA(cudaFree(hks->stage_d));
+                hks->stage_d = nullptr;
+            }
+            OFHE_CUDA(cudaMalloc(&hks->stage_d, 3 * S_ * words * sizeof(uint64_t)));
+            hks->stage_words = 3 * S_ * words;
+        }
+        if (!hks->s_comp) {
+            OFHE_CUDA(cudaStreamCreateWithFlags(&hks->s_h2d, cudaStreamNonBlocking));
+            OFHE_CUDA(cudaStreamCreateWithFlags(&hks->s_d2h, cudaStreamNonBlocking));
+            OFHE_CUDA(cudaStreamCreateWithFlags(&hks->s_comp, cudaStreamNonBlocking));
+            for (int i = 0; i < S_; ++i) {
+                OFHE_CUDA(cudaEventCreateWithFlags(&hks->ev_in[i], cudaEventDisableTiming));
+                OFHE_CUDA(cudaEventCreateWithFlags(&hks->ev_comp[i], cudaEventDisableTiming));
+                OFHE_CUDA(cudaEventCreateWithFlags(&hks->ev_out[i], cudaEventDisableTiming));
+            }
+        }
+        OFHE_CUDA(cudaDeviceSynchronize());  // the staging buffers / scratch may be in use by earlier stream work
+        for (uint32_t k = 0; k < n; ++k) {
+            const int sl = k % S_;
+            uint64_t *d1 = hks->stage_d + (size_t)sl * 3 * words, *d2 = d1 + words, *d3 = d2 + words;
+            if (k >= (uint32_t)S_)  // slot inputs are free once the multiplication that used them has run
+                OFHE_CUDA(cudaStreamWaitEvent(hks->s_h2d, hks->ev_comp[sl], 0));
+            OFHE_CUDA(cudaMemcpyAsync(d1, ct1_h[k], bytes, cudaMemcpyHostToDevice, hks->s_h2d));
+            OFHE_CUDA(cudaMemcpyAsync(d2, ct2_h[k], bytes, cudaMemcpyHostToDevice, hks->s_h2d));
+            OFHE_CUDA(cudaEventRecord(hks->ev_in[sl], hks->s_h2d));
+            OFHE_CUDA(cudaStreamWaitEvent(hks->s_comp, hks->ev_in[sl], 0));
+            if (k >= (uint32_t)S_)  // the slot's previous result must have left before it is overwritten
+                OFHE_CUDA(cudaStreamWaitEvent(hks->s_comp, hks->ev_out[sl], 0));
+            h.evalmult(sizeQl, d1, d2, *evk->k, d3, hks->s_comp);
+            OFHE_CUDA(cudaEventRecord(hks->ev_comp[sl], hks->s_comp));
+            OFHE_CUDA(cudaStreamWaitEvent(hks->s_d2h, hks->ev_comp[sl], 0));
+            OFHE_CUDA(cudaMemcpyAsync(out_h[k], d3, bytes, cudaMemcpyDeviceToHost, hks->s_d2h));
+            OFHE_CUDA(cudaEventRecord(hks->ev_out[sl], hks->s_d2h));
+        }
+        OFHE_CUDA(cudaStreamSynchronize(hks->s_d2h));
+        OFHE_CUDA(cudaStreamSynchronize(hks->s_comp));
     });
 }
 int ofhe_ckks_rescale(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_d, uint64_t* out_d, uint32_t n_polys,

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ofhe_hks_keyswitch_core": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_ckks_evalmult": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_ckks_evalmult_host": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_evalmult_host_batch": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_ckks_rescale": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp]),
     "ofhe_ckks_rotate": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_find_automorphism_index": (C.c_uint32, [C.c_int32, C.c_uint32]),
@@ -355,6 +356,12 @@ class Hks:
     def evalmult_host(self, sizeQl, ct1, ct2, evk, out):
         """numpy (or pinned torch CPU) buffers in, numpy out: host<->device copies included."""
         _ck(lib().ofhe_ckks_evalmult_host(self.h, sizeQl, _ptr(ct1), _ptr(ct2), evk.h, _ptr(out)))
+
+    def evalmult_host_batch(self, sizeQl, ct1s, ct2s, evk, outs):
+        """n independent multiplications on (pinned) host buffers, H2D / compute / D2H software-pipelined."""
+        n = len(ct1s)
+        arr = lambda xs: (C.c_void_p * n)(*[_ptr(x) for x in xs])
+        _ck(lib().ofhe_ckks_evalmult_host_batch(self.h, sizeQl, n, arr(ct1s), arr(ct2s), evk.h, arr(outs)))
 
     def rescale(self, sizeQl, src, dst, n_polys=2):
         _ck(lib().ofhe_ckks_rescale(self.h, sizeQl, _ptr(src), _ptr(dst), n_polys, _stream()))

@@ -245,6 +245,13 @@ def test_hybrid_keyswitch_golden(gpu, golden, name):
         hks.evalmult_host(sizeQl, np.ascontiguousarray(g[f"l{sizeQl}_ct1"]), np.ascontiguousarray(g[f"l{sizeQl}_ct2"]),
                           evk, oh)
         assert (oh == g[f"l{sizeQl}_evalmult"]).all()
+        # and through the software-pipelined batch entry point (more operations than staging slots)
+        a1 = np.ascontiguousarray(g[f"l{sizeQl}_ct1"])
+        a2 = np.ascontiguousarray(g[f"l{sizeQl}_ct2"])
+        outs = [np.zeros((2, sizeQl, N), dtype=np.uint64) for _ in range(7)]
+        hks.evalmult_host_batch(sizeQl, [a1, a2] + [a1] * 5, [a2, a1] + [a2] * 5, evk, outs)
+        for o in outs:  # the tensor product is symmetric in its two arguments
+            assert (o == g[f"l{sizeQl}_evalmult"]).all()
         if sizeQl > 1:
             r = ctx.zeros(2, sizeQl - 1, N)
             hks.rescale(sizeQl, ctx.upload(g[f"l{sizeQl}_ct1"]), r, 2)
