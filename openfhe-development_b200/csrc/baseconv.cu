@@ -28,7 +28,13 @@ namespace ofhe {
 namespace {
 
 constexpr uint32_t kMask30 = (1u << 30) - 1;
-constexpr int kJPT         = 8;    // target limbs per thread
+#ifndef OFHE_BCONV_JPT
+#define OFHE_BCONV_JPT 8
+#endif
+#ifndef OFHE_BCONV_MINB
+#define OFHE_BCONV_MINB 1
+#endif
+constexpr int kJPT         = OFHE_BCONV_JPT;  // target limbs per thread
 constexpr int kThreads     = 128;  // coefficients per CTA
 
 struct BConvDev {
@@ -65,8 +71,8 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
 
 // CH chunks of 16 source limbs; kCPT coefficients per thread (2 when the register budget allows: every 128-bit
 // matrix read from shared memory then feeds 16 IMADs)
-template <int CH, int kCPT>
-__global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, LimbMap qmap, LimbMap pmap,
+template <int CH, int kCPT, int MODE>  // MODE is a template parameter so that the a10 instance carries no floating-point code
+__global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDev r, BConvDev t, LimbMap qmap, LimbMap pmap,
                                                           PosMap xomap, const uint64_t* __restrict__ in,
                                                           uint64_t* __restrict__ out, size_t in_stride,
                                                           size_t out_stride, int premultiplied) {
@@ -108,10 +114,10 @@ __global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, 
         for (int i = 0; i < MAXQ; ++i) {
             const int ii = i < (int)t.sizeQ ? i : 0;  // padded rows re-read row 0 and are zeroed
             uint64_t y   = in[(size_t)qmap.pos[ii] * N + rr];
-            if (!premultiplied && t.mode != 2)
+            if (!premultiplied && MODE != 2)
                 y = shoup(y, s_src[3 * ii + 1], s_src[3 * ii + 2], s_src[3 * ii]);
             y        = i < (int)t.sizeQ ? y : 0;
-            if (t.mode != 0 && i < (int)t.sizeQ)
+            if (MODE != 0 && i < (int)t.sizeQ)
                 nu[c] = __dadd_rn(nu[c], __dmul_rn(__ull2double_rn(y), t.dbl[i]));
             y0[c][i] = (uint32_t)y & kMask30;
             y1[c][i] = (uint32_t)(y >> 30);
@@ -173,11 +179,11 @@ __global__ void __launch_bounds__(kThreads) bconv_kernel(RingDev r, BConvDev t, 
                     const uint32_t jj = j0 + j + o;
                     const uint64_t p  = d[0];
                     uint64_t v        = csub(lazy_reduce_n(total[c][o], d[5], 0 - p), p);
-                    if (t.mode == 1) {  // dcrtpoly-impl.h:1060,1073: minus alphaQModp[(size_t)nu][j]
+                    if (MODE == 1) {  // dcrtpoly-impl.h:1060,1073: minus alphaQModp[(size_t)nu][j]
                         const uint64_t a = t.alpha[(size_t)__double2ull_rz(nu[c]) * t.sizeP + jj];
                         v                = submod(v, a, p);
                     }
-                    else if (t.mode == 2) {  // dcrtpoly-impl.h:1550-1586
+                    else if (MODE == 2) {  // dcrtpoly-impl.h:1550-1586
                         const ModConst mc = r.mc[pmap.idx[jj]];
                         const uint64_t xo = in[(size_t)xomap.pos[jj] * N + rr];
                         v                 = addmod(v, mulmod(xo, t.extra[jj], mc), p);
@@ -216,19 +222,30 @@ void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* o
         const char* e = getenv("OFHE_BCONV_CPT");  // tuning knob: coefficients per thread for <= 16 source limbs
         return e ? atoi(e) : 1;
     }();
-    const int cpt = t.sizeQ <= 16 ? (cpt1 == 1 ? 1 : 2) : 1;
+    const int cpt = (t.sizeQ <= 16 && t.mode == 0) ? (cpt1 == 1 ? 1 : 2) : 1;
     dim3 grid((r.N + kThreads * cpt - 1) / (kThreads * cpt), (t.sizeP + kJPT - 1) / kJPT, batch);
     const int pm = premultiplied ? 1 : 0;
-    if (t.sizeQ <= 16 && cpt == 2)
-        bconv_kernel<1, 2><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
-    else if (t.sizeQ <= 16)
-        bconv_kernel<1, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
-    else if (t.sizeQ <= 32)
-        bconv_kernel<2, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
-    else if (t.sizeQ <= 48)
-        bconv_kernel<3, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
+#define OFHE_BCONV_LAUNCH(CH, CPT, MODE) \
+    bconv_kernel<CH, CPT, MODE><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm)
+#define OFHE_BCONV_BY_SIZE(MODE)            \
+    do {                                    \
+        if (t.sizeQ <= 16)                  \
+            OFHE_BCONV_LAUNCH(1, 1, MODE);  \
+        else if (t.sizeQ <= 32)             \
+            OFHE_BCONV_LAUNCH(2, 1, MODE);  \
+        else if (t.sizeQ <= 48)             \
+            OFHE_BCONV_LAUNCH(3, 1, MODE);  \
+        else                                \
+            OFHE_BCONV_LAUNCH(4, 1, MODE);  \
+    } while (0)
+    if (t.mode == 0 && t.sizeQ <= 16 && cpt == 2)
+        OFHE_BCONV_LAUNCH(1, 2, 0);
+    else if (t.mode == 0)
+        OFHE_BCONV_BY_SIZE(0);
+    else if (t.mode == 1)
+        OFHE_BCONV_BY_SIZE(1);
     else
-        bconv_kernel<4, 1><<<grid, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pm);
+        OFHE_BCONV_BY_SIZE(2);
     OFHE_CUDA(cudaGetLastError());
 }
 
