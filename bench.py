@@ -124,6 +124,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="N>1: limb exchange by NVLink peer stores fused into the INTT (default) or NCCL all-gathers")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="N>1 push mode: eager launches, no CUDA graphs")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,17 +236,45 @@ def main():
         ring.fill_uniform(ct1.view(2 * nq, N), own_q * 2, 11)
         ring.fill_uniform(ct2.view(2 * nq, N), own_q * 2, 12)
         outs = [ctx.zeros(2, nq, N) for _ in range(n_slots)]
-        gqs = [ctx.zeros(world, info["slots_q"], N) for _ in range(n_slots)]
-        gps = [ctx.zeros(world, 2, info["slots_p"], N) for _ in range(n_slots)]
         streams = [torch.cuda.Stream() for _ in range(n_slots)]
 
-        def all_gather(buf):
-            dist.all_gather_into_tensor(buf, buf[rank])  # in place: the send segment is this rank's slice of buf
+        def exchange_obj(obj):
+            objs = [None] * world
+            dist.all_gather_object(objs, obj)
+            return objs
+
+        graphs = [None] * n_slots
+        if a.exchange == "push":
+            # the INTT's last pass stores each rank's rows into every rank's gather buffer over NVLink (CUDA-IPC
+            # mappings), a one-CTA device barrier replaces the collective's completion: no NCCL call on the data path
+            pqs = [m.PeerBuffers(ctx, world * info["slots_q"] * N, rank, world, exchange_obj) for _ in range(n_slots)]
+            pps = [m.PeerBuffers(ctx, world * 2 * info["slots_p"] * N, rank, world, exchange_obj) for _ in range(n_slots)]
+            pfl = m.PeerBuffers(ctx, m.lib().ofhe_peer_flags_words(world, 2 * n_slots), rank, world, exchange_obj)
+            peer_bufs = pqs + pps + [pfl]
+            dist.barrier()
+
+            def one(s, c1=None, c2=None):
+                shards[s].evalmult_push(sizeQl, ct1 if c1 is None else c1, ct2 if c2 is None else c2, ea, eb, outs[s],
+                                        pqs[s].array, pps[s].array, pfl.array, slot=s)
+        else:
+            gqs = [ctx.zeros(world, info["slots_q"], N) for _ in range(n_slots)]
+            gps = [ctx.zeros(world, 2, info["slots_p"], N) for _ in range(n_slots)]
+            peer_bufs = []
+
+            def all_gather(buf):
+                dist.all_gather_into_tensor(buf, buf[rank])  # in place: the send segment is this rank's slice of buf
+
+            def one(s, c1=None, c2=None):
+                shards[s].evalmult(sizeQl, ct1 if c1 is None else c1, ct2 if c2 is None else c2, ea, eb, outs[s],
+                                   gqs[s], gps[s], all_gather)
 
         def step(k):
             s = k % n_slots
             with torch.cuda.stream(streams[s]):
-                shards[s].evalmult(sizeQl, ct1, ct2, ea, eb, outs[s], gqs[s], gps[s], all_gather)
+                if graphs[s] is not None:
+                    graphs[s].replay()
+                else:
+                    one(s)
 
         def run(nsteps):
             cur = torch.cuda.current_stream()
@@ -255,6 +286,23 @@ def main():
                 cur.wait_stream(st)
 
         run(max(a.warmup, n_slots))
+        if a.exchange == "push" and a.graph:
+            # one CUDA graph per pipeline slot (all launches of a multiplication incl. the device barriers, whose epochs
+            # live in device memory): removes the per-launch host cost that dominates once the work is split 8 ways
+            torch.cuda.synchronize()
+            dist.barrier()
+            try:
+                for s_ in range(n_slots):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=streams[s_]):
+                        one(s_)
+                    graphs[s_] = g
+            except Exception as ex:  # capture unsupported: stay on eager launches
+                graphs = [None] * n_slots
+                print(f"[bench] CUDA graph capture failed, eager launches: {ex}", file=sys.stderr)
+            torch.cuda.synchronize()
+            dist.barrier()
+            run(n_slots)
         barrier()
         sampler.start()
         e0.record()
@@ -264,8 +312,11 @@ def main():
         sampler.stop_flag.set()
         ms = max_over_ranks(e0.elapsed_time(e1))
         value = a.steps / (ms * 1e-3)
-        parallelism, scaling = f"RNS limbs sharded over {world} GPUs, 2 NCCL all-gathers per EvalMult, 2 pipeline slots", "strong"
-        launches = LAUNCHES_PER_STEP
+        how = ("exchange by NVLink peer stores fused into the INTT + device barriers"
+               + (", one CUDA graph per slot" if graphs[0] is not None else "")) if a.exchange == "push" \
+            else "2 NCCL all-gathers per EvalMult"
+        parallelism, scaling = f"RNS limbs sharded over {world} GPUs, {how}, {n_slots} pipeline slots", "strong"
+        launches = 18 if a.exchange == "push" else LAUNCHES_PER_STEP
         # ---- end to end: every rank moves its own limb rows host<->device around the sharded multiplication
         h1 = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
         h2 = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
@@ -278,7 +329,7 @@ def main():
         def e2e_step():
             d1.copy_(h1, non_blocking=True)
             d2.copy_(h2, non_blocking=True)
-            shards[0].evalmult(sizeQl, d1, d2, ea, eb, outs[0], gqs[0], gps[0], all_gather)
+            one(0, d1, d2)
             ho.copy_(outs[0], non_blocking=True)
             torch.cuda.synchronize()
 
@@ -289,7 +340,11 @@ def main():
         for _ in range(e2e_steps):
             e2e_step()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        closers = shards
+        closers = shards + peer_bufs
+        if a.exchange == "push":
+            torch.cuda.synchronize()
+            dist.barrier()
+            assert ctx.peer_barrier_timeouts(pfl.local, world, 2 * n_slots) == 0, "device barrier timed out"
     ct_bytes = 2 * sizeQl * N * 8
 
     # ---- roofline of the dominant kernel family: forward limb-NTT on a slab larger than L2 ---------------------
@@ -317,7 +372,7 @@ def main():
     line = None
     if rank == 0:
         base = None
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:  # the CPU arm is timed at N=1 only (the ranks would fight for the cores)
             base, _ = cpu_reference_run(a.cpu_steps, 1)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms / a.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="u64",

@@ -208,6 +208,34 @@ int ofhe_shard_evalmult_b(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gather
                           const uint64_t* evk_b_d, uint64_t* gatherP_d, void* stream);
 int ofhe_shard_evalmult_c(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gatherP_d, uint64_t* out_d, void* stream);
 
+/* ---- the same exchange WITHOUT a collective call: the last pass of the inverse NTT that produces a rank's rows
+ *      stores them into every rank's gather buffer directly (NVLink peer stores; the transfer overlaps the transform),
+ *      and a one-CTA device barrier replaces the all-gather's completion.  `*_of_rank_h` are HOST arrays of `world`
+ *      DEVICE pointers, entry r = rank r's buffer as mapped in THIS process (own allocation for r == rank, an
+ *      ofhe_ipc_import()ed mapping otherwise; plain pointers when several virtual ranks share one process).
+ *      Sequence per multiplication: a_push, peer_barrier(index 2*slot), b_push, peer_barrier(2*slot+1), c.
+ *      Buffers may be reused for the next multiplication on the same stream without further synchronisation: every
+ *      rank passed the second barrier only after all ranks finished reading gatherQ, and passes the next first barrier
+ *      only after all ranks finished reading gatherP (multi-GPU).                                          */
+int ofhe_shard_evalmult_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct1_d, const uint64_t* ct2_d,
+                               uint64_t* out_d, uint64_t* const* gatherQ_of_rank_h, void* stream);
+int ofhe_shard_evalmult_b_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* evk_a_d, const uint64_t* evk_b_d,
+                               uint64_t* const* gatherQ_of_rank_h, uint64_t* const* gatherP_of_rank_h, void* stream);
+/* flags buffers: ofhe_peer_flags_words(world, n_barriers) zero-initialised words per rank.  The kernel bumps this
+ * rank's epoch for barrier `index`, publishes it to every rank (release, system scope) and waits until every rank's
+ * arrival for that epoch is visible (acquire).  A wait longer than ~2 s gives up and counts a timeout (readable with
+ * ofhe_peer_barrier_timeouts) instead of hanging the GPU.                                                            */
+size_t ofhe_peer_flags_words(uint32_t world, uint32_t n_barriers);
+int ofhe_peer_barrier(ofhe_ctx* ctx, uint64_t* const* flags_of_rank_h, uint32_t world, uint32_t rank, uint32_t index,
+                      void* stream);
+int ofhe_peer_barrier_timeouts(ofhe_ctx* ctx, const uint64_t* flags_d, uint32_t world, uint32_t n_barriers,
+                               uint64_t* count_out);
+/* CUDA IPC for ofhe_malloc()ed buffers (one process per GPU): export a 64-byte handle, import it in another process
+ * (enables peer access), release the mapping.                                                                        */
+int ofhe_ipc_export(ofhe_ctx* ctx, void* dptr, void* handle64_out);
+int ofhe_ipc_import(ofhe_ctx* ctx, const void* handle64, void** dptr_out);
+int ofhe_ipc_release(ofhe_ctx* ctx, void* dptr);
+
 /* fills dst_d [n_limbs][N] with uniform residues in [0, q_l) from a counter-based generator (synthetic inputs) */
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
                       void* stream);

@@ -763,6 +763,123 @@ int ofhe_shard_evalmult_c(ofhe_shard* s, uint32_t sizeQl, const uint64_t* gather
     });
 }
 
+namespace {
+PeerOut peer_list(const Shard& sh, uint64_t* const* of_rank) {
+    if (sh.world > kMaxPeers)
+        throw Error("peer push supports at most 8 ranks");
+    PeerOut po;
+    po.n = sh.world;
+    for (uint32_t r = 0; r < sh.world; ++r) {
+        if (!of_rank[r])
+            throw Error("null peer buffer");
+        po.base[r] = of_rank[r];
+    }
+    return po;
+}
+struct PeerFlags {
+    uint64_t* base[kMaxPeers];
+};
+// flags layout per rank: [n_barriers][world + 2] = arrivals from each rank | this rank's epoch | timeout count
+__global__ void peer_barrier_kernel(PeerFlags pf, uint32_t world, uint32_t rank, uint32_t index) {
+    const uint32_t row = index * (world + 2);
+    uint64_t* mine     = pf.base[rank] + row;
+    __shared__ uint64_t epoch_s;
+    if (threadIdx.x == 0) {
+        epoch_s     = mine[world] + 1;
+        mine[world] = epoch_s;
+    }
+    __syncthreads();
+    const uint64_t epoch = epoch_s;
+    if (threadIdx.x < world) {
+        // everything this rank stored to its peers (previous kernels on this stream) is ordered before the flag
+        __threadfence_system();
+        uint64_t* theirs = pf.base[threadIdx.x] + row + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+        const uint64_t* arrive = mine + threadIdx.x;
+        const long long t0     = clock64();
+        uint64_t seen          = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
+            if (seen >= epoch)
+                break;
+            if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz: give up rather than hang the device
+                atomicAdd(reinterpret_cast<unsigned long long*>(mine + world + 1), 1ULL);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+}  // namespace
+
+int ofhe_shard_evalmult_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct1_d, const uint64_t* ct2_d,
+                               uint64_t* out_d, uint64_t* const* gatherQ_of_rank_h, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        const PeerOut po = peer_list(*s->s, gatherQ_of_rank_h);
+        s->s->evalmult_a(sizeQl, ct1_d, ct2_d, out_d, po.base[s->s->rank], S(stream), &po);
+    });
+}
+int ofhe_shard_evalmult_b_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* evk_a_d, const uint64_t* evk_b_d,
+                               uint64_t* const* gatherQ_of_rank_h, uint64_t* const* gatherP_of_rank_h, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        const PeerOut po = peer_list(*s->s, gatherP_of_rank_h);
+        s->s->evalmult_b(sizeQl, gatherQ_of_rank_h[s->s->rank], evk_a_d, evk_b_d, po.base[s->s->rank], S(stream), &po);
+    });
+}
+size_t ofhe_peer_flags_words(uint32_t world, uint32_t n_barriers) {
+    return (size_t)n_barriers * (world + 2);
+}
+int ofhe_peer_barrier(ofhe_ctx* ctx, uint64_t* const* flags_of_rank_h, uint32_t world, uint32_t rank, uint32_t index,
+                      void* stream) {
+    return guard([&] {
+        if (world == 0 || world > kMaxPeers || rank >= world)
+            throw Error("peer barrier: bad world / rank");
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        PeerFlags pf;
+        for (uint32_t r = 0; r < world; ++r)
+            pf.base[r] = flags_of_rank_h[r];
+        peer_barrier_kernel<<<1, 32, 0, S(stream)>>>(pf, world, rank, index);
+        OFHE_CUDA(cudaGetLastError());
+    });
+}
+int ofhe_peer_barrier_timeouts(ofhe_ctx* ctx, const uint64_t* flags_d, uint32_t world, uint32_t n_barriers,
+                               uint64_t* count_out) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        std::vector<uint64_t> h(ofhe_peer_flags_words(world, n_barriers));
+        OFHE_CUDA(cudaMemcpy(h.data(), flags_d, sizeof(uint64_t) * h.size(), cudaMemcpyDeviceToHost));
+        uint64_t n = 0;
+        for (uint32_t b = 0; b < n_barriers; ++b)
+            n += h[(size_t)b * (world + 2) + world + 1];
+        *count_out = n;
+    });
+}
+int ofhe_ipc_export(ofhe_ctx* ctx, void* dptr, void* handle64_out) {
+    return guard([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        cudaIpcMemHandle_t h;
+        OFHE_CUDA(cudaIpcGetMemHandle(&h, dptr));
+        std::memcpy(handle64_out, &h, sizeof(h));
+    });
+}
+int ofhe_ipc_import(ofhe_ctx* ctx, const void* handle64, void** dptr_out) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, sizeof(h));
+        OFHE_CUDA(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+int ofhe_ipc_release(ofhe_ctx* ctx, void* dptr) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaIpcCloseMemHandle(dptr));
+    });
+}
+
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
                       void* stream) {
     return guard([&] {

@@ -27,6 +27,15 @@ struct PosMap {  // output rows when a transform writes to a differently laid-ou
     uint16_t pos[kMaxLimbs];
 };
 
+// Destinations of a transform's FINAL pass when the result is pushed to several buffers at once (this rank's gather
+// buffer and, over NVLink peer mappings, the same rows of every other rank's): shard.cu / ofhe_shard_*_push.
+constexpr uint32_t kMaxPeers = 8;
+struct PeerOut {
+    uint64_t* base[kMaxPeers];
+    uint32_t n = 0;
+};
+
+
 // device view of a ring: tables of every registered modulus
 struct RingDev {
     const ModConst* mc;     // [n_moduli]
@@ -100,7 +109,7 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
 // `fold` (device, [lm.n][4]): per-limb replacement for (nInv, Shoup, Tinv[1]*nInv, Shoup) with an extra scalar
 // folded in, see make_inv_fold(); nullptr = plain inverse transform.
 void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
-                    const PosMap* out_pos = nullptr, const uint64_t* fold = nullptr);
+                    const PosMap* out_pos = nullptr, const uint64_t* fold = nullptr, const PeerOut* peers = nullptr);
 // host helper: the four folded constants of limb `mod_idx` for extra scalar s
 void make_inv_fold(const Ring& r, uint32_t mod_idx, uint64_t s, uint64_t out4[4]);
 

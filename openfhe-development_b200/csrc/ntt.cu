@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_strided(RingDev r, const uint64_t
 
 template <int A>
 __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data, LimbMap lm,
-                                                        const uint64_t* __restrict__ fold) {
+                                                        const uint64_t* __restrict__ fold, PeerOut po) {
     const uint32_t limb   = blockIdx.y;
     const uint32_t mi     = lm.idx[limb];
     const uint32_t stride = r.N >> A;
@@ -175,9 +175,20 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data
         x[k] = p[(size_t)k * stride];
     gs_round<A, true>(x, r.tw_inv + (size_t)mi * r.N, 1u, last_const(mc, fold, limb), m);
     // every point passed through the folded last stage => already canonical
+    if (po.n == 0) {
 #pragma unroll
-    for (int k = 0; k < (1 << A); ++k)
-        p[(size_t)k * stride] = x[k];
+        for (int k = 0; k < (1 << A); ++k)
+            p[(size_t)k * stride] = x[k];
+    }
+    else {  // push the finished rows into every destination buffer (local one included)
+        const size_t off = (size_t)lm.pos[limb] * r.N + c;
+        for (uint32_t d = 0; d < po.n; ++d) {
+            uint64_t* q = po.base[d] + off;
+#pragma unroll
+            for (int k = 0; k < (1 << A); ++k)
+                q[(size_t)k * stride] = x[k];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_fwd_tile(RingDev r, c
 template <bool SINGLE>  // SINGLE: logN == 12, the folded last stage happens in round A
 __global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_inv_tile(RingDev r, const uint64_t* in,
                                                      uint64_t* out, LimbMap lm, PosMap op,
-                                                     const uint64_t* __restrict__ fold) {
+                                                     const uint64_t* __restrict__ fold, PeerOut po) {
     __shared__ uint64_t sm[kTile];
     const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
     const uint32_t mi = lm.idx[limb];
@@ -281,9 +292,17 @@ __global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_inv_tile(RingDev r, c
     for (int k = 0; k < 16; ++k)
         x[k] = sm[t + 256 * k];
     gs_round<4, SINGLE>(x, tw, (1u << s0) + tile, lc, m);
+    if (!SINGLE || po.n == 0) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-        out[obase + t + 256 * k] = x[k];  // SINGLE: canonical; else lazy [0,2q), finished by the strided kernel
+        for (int k = 0; k < 16; ++k)
+            out[obase + t + 256 * k] = x[k];  // SINGLE: canonical; else lazy [0,2q), finished by the strided kernel
+    }
+    else {
+        for (uint32_t d = 0; d < po.n; ++d)
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                po.base[d][obase + t + 256 * k] = x[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,7 +310,7 @@ __global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_inv_tile(RingDev r, c
 // one stage per barrier.  Not a performance path.
 template <bool INV>
 __global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap lm, PosMap op,
-                          const uint64_t* __restrict__ fold) {
+                          const uint64_t* __restrict__ fold, PeerOut po) {
     extern __shared__ uint64_t s[];
     const uint32_t limb = lm.pos[blockIdx.x], olimb = op.pos[blockIdx.x], mi = lm.idx[blockIdx.x], N = r.N;
     const ModConst mc = r.mc[mi];
@@ -324,8 +343,13 @@ __global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap 
         const LastConst lc = last_const(mc, fold, blockIdx.x);
         for (uint32_t j = threadIdx.x; j < h; j += blockDim.x) {
             uint64_t a = s[j] + s[j + h], e = s[j] - s[j + h] + twoq;
-            out[(size_t)olimb * N + j]     = shoup(a, lc.a, lc.as, q);
-            out[(size_t)olimb * N + j + h] = shoup(e, lc.b, lc.bs, q);
+            a = shoup(a, lc.a, lc.as, q);
+            e = shoup(e, lc.b, lc.bs, q);
+            for (uint32_t d = 0; d < (po.n ? po.n : 1u); ++d) {
+                uint64_t* o = po.n ? po.base[d] : out;
+                o[(size_t)olimb * N + j]     = a;
+                o[(size_t)olimb * N + j + h] = e;
+            }
         }
     }
 }
@@ -347,12 +371,12 @@ void fwd_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm
 }
 template <int A>
 void inv_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op,
-             const uint64_t* fold, cudaStream_t st) {
+             const uint64_t* fold, const PeerOut& po, cudaStream_t st) {
     dim3 g2(r.N / kTile, lm.n);
-    ntt_inv_tile<false><<<g2, 256, 0, st>>>(r.dev(), in, out, lm, op, nullptr);
+    ntt_inv_tile<false><<<g2, 256, 0, st>>>(r.dev(), in, out, lm, op, nullptr, PeerOut{});
     const uint32_t stride = r.N >> A;
     dim3 g1((stride + 255) / 256, lm.n);
-    ntt_inv_strided<A><<<g1, 256, 0, st>>>(r.dev(), out, on_output(lm, op), fold);
+    ntt_inv_strided<A><<<g1, 256, 0, st>>>(r.dev(), out, on_output(lm, op), fold, po);
 }
 PosMap default_pos(const LimbMap& lm, const PosMap* out_pos) {
     if (out_pos)
@@ -372,7 +396,7 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
     const PosMap op = default_pos(lm, out_pos);
     if (r.logN < 12) {
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
-        ntt_small<false><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, nullptr);
+        ntt_small<false><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, nullptr, PeerOut{});
     }
     else if (r.logN == 12) {
         ntt_fwd_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op);
@@ -391,24 +415,25 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
 }
 
 void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
-                    const PosMap* out_pos, const uint64_t* fold) {
+                    const PosMap* out_pos, const uint64_t* fold, const PeerOut* peers) {
     if (lm.n == 0)
         return;
     const PosMap op = default_pos(lm, out_pos);
+    const PeerOut po = peers ? *peers : PeerOut{};
     if (r.logN < 12) {
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
-        ntt_small<true><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, fold);
+        ntt_small<true><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, fold, po);
     }
     else if (r.logN == 12) {
-        ntt_inv_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op, fold);
+        ntt_inv_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op, fold, po);
     }
     else {
         switch (r.logN - 12) {
-            case 1: inv_big<1>(r, in, out, lm, op, fold, st); break;
-            case 2: inv_big<2>(r, in, out, lm, op, fold, st); break;
-            case 3: inv_big<3>(r, in, out, lm, op, fold, st); break;
-            case 4: inv_big<4>(r, in, out, lm, op, fold, st); break;
-            case 5: inv_big<5>(r, in, out, lm, op, fold, st); break;
+            case 1: inv_big<1>(r, in, out, lm, op, fold, po, st); break;
+            case 2: inv_big<2>(r, in, out, lm, op, fold, po, st); break;
+            case 3: inv_big<3>(r, in, out, lm, op, fold, po, st); break;
+            case 4: inv_big<4>(r, in, out, lm, op, fold, po, st); break;
+            case 5: inv_big<5>(r, in, out, lm, op, fold, po, st); break;
             default: throw Error("ring dimension above 2^17 is not supported");
         }
     }

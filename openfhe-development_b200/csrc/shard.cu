@@ -190,7 +190,7 @@ size_t Shard::workspace_words(uint32_t sizeQl) {
 }
 
 void Shard::evalmult_a(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out, uint64_t* gatherQ,
-                       cudaStream_t st) {
+                       cudaStream_t st, const PeerOut* peers) {
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, P = (size_t)lv.nOwnQ * N;
@@ -199,11 +199,11 @@ void Shard::evalmult_a(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2
     if (lv.nOwnQ == 0)
         return;
     launch_tensor(r, ct1, ct1 + P, ct2, ct2 + P, out, out + P, c2, lv.map_q, st);  // base-leveledshe.cpp:620-624
-    launch_ntt_inv(r, c2, gatherQ, lv.map_q, st, &lv.gatherq_pos, lv.fold_q_d);    // keyswitch-hybrid.cpp:359
+    launch_ntt_inv(r, c2, gatherQ, lv.map_q, st, &lv.gatherq_pos, lv.fold_q_d, peers);  // keyswitch-hybrid.cpp:359
 }
 
 void Shard::evalmult_b(uint32_t sizeQl, const uint64_t* gatherQ, const uint64_t* evk_a, const uint64_t* evk_b,
-                       uint64_t* gatherP, cudaStream_t st) {
+                       uint64_t* gatherP, cudaStream_t st, const PeerOut* peers) {
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, nq = lv.nOwnQ, np = ownP.size(), nown = nq + np;
@@ -226,7 +226,7 @@ void Shard::evalmult_b(uint32_t sizeQl, const uint64_t* gatherQ, const uint64_t*
     launch_ks_inner_product(r, lv.n_digits, digits, nown * N, evk_a, evk_b, (size_t)(nOwnQFull + np) * N, (uint32_t)nq,
                             (uint32_t)(nOwnQFull - nq), e01, e01 + nown * N, lv.map_qp, st);
     if (np)
-        launch_ntt_inv(r, e01, gatherP, lv.map_p2_src, st, &lv.gatherp_pos, lv.fold_p_d);  // dcrtpoly-impl.h:976-984
+        launch_ntt_inv(r, e01, gatherP, lv.map_p2_src, st, &lv.gatherp_pos, lv.fold_p_d, peers);  // dcrtpoly-impl.h:976-984
 }
 
 void Shard::evalmult_c(uint32_t sizeQl, const uint64_t* gatherP, uint64_t* out, cudaStream_t st) {

@@ -42,12 +42,14 @@ struct Shard {
     Level& level(uint32_t sizeQl);
     size_t workspace_words(uint32_t sizeQl);
     // phase A: tensor product on the owned limbs (out = c0 | c1), INTT(c2) * QHatInv into this rank's rows of gatherQ
+    // `peers` (optional): the same gather buffer of EVERY rank, peer-mapped; the finished rows are then written into all
+    // of them by the INTT's last pass (the exchange rides on the kernel's own stores over NVLink, no collective call)
     void evalmult_a(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out, uint64_t* gatherQ,
-                    cudaStream_t st);
+                    cudaStream_t st, const PeerOut* peers = nullptr);
     // phase B (after the all-gather of gatherQ): ModUp into the owned rows, NTT, evk inner product, INTT of the owned
     // P rows * PHatInv into this rank's rows of gatherP
     void evalmult_b(uint32_t sizeQl, const uint64_t* gatherQ, const uint64_t* evk_a, const uint64_t* evk_b,
-                    uint64_t* gatherP, cudaStream_t st);
+                    uint64_t* gatherP, cudaStream_t st, const PeerOut* peers = nullptr);
     // phase C (after the all-gather of gatherP): ModDown of the owned Q rows and the final additions into out
     void evalmult_c(uint32_t sizeQl, const uint64_t* gatherP, uint64_t* out, cudaStream_t st);
 };

@@ -78,6 +78,14 @@ SIGNATURES = {
     "ofhe_shard_evalmult_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_b": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_c": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_shard_evalmult_a_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_evalmult_b_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_peer_flags_words": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+    "ofhe_peer_barrier": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "ofhe_peer_barrier_timeouts": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _u64p]),
+    "ofhe_ipc_export": (C.c_int, [_vp, _vp, _vp]),
+    "ofhe_ipc_import": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "ofhe_ipc_release": (C.c_int, [_vp, _vp]),
     "ofhe_fill_uniform": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp]),
 }
 
@@ -122,6 +130,11 @@ def _ptr(x):
 
 def _idx(a):
     return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers (the `*_of_rank_h` arguments)."""
+    return (C.c_void_p * len(ptrs))(*[int(_ptr(p)) for p in ptrs])
 
 
 def _stream():
@@ -191,6 +204,46 @@ class Context:
     @staticmethod
     def download(t):
         return t.detach().cpu().numpy().view(np.uint64)
+
+    # raw cudaMalloc buffers (zero-filled) for the peer-push exchange: IPC handles exist only for whole allocations
+    def raw_zeros(self, words):
+        p = _vp()
+        _ck(lib().ofhe_malloc(self.h, 8 * int(words), C.byref(p)))
+        z = np.zeros(int(words), dtype=np.uint64)
+        _ck(lib().ofhe_memcpy_h2d(self.h, p, z.ctypes.data, z.nbytes, None))
+        _ck(lib().ofhe_stream_sync(self.h, None))
+        return p.value
+
+    def raw_free(self, ptr):
+        _ck(lib().ofhe_free(self.h, ptr))
+
+    def raw_download(self, ptr, words):
+        o = np.empty(int(words), dtype=np.uint64)
+        _ck(lib().ofhe_memcpy_d2h(self.h, o.ctypes.data, ptr, o.nbytes, None))
+        _ck(lib().ofhe_stream_sync(self.h, None))
+        return o
+
+    def ipc_export(self, ptr):
+        h = C.create_string_buffer(64)
+        _ck(lib().ofhe_ipc_export(self.h, ptr, h))
+        return h.raw
+
+    def ipc_import(self, handle):
+        p = _vp()
+        _ck(lib().ofhe_ipc_import(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_release(self, ptr):
+        _ck(lib().ofhe_ipc_release(self.h, ptr))
+
+    def peer_barrier(self, flags_of_rank, rank, index):
+        """flags_of_rank: ctypes array from ptr_array()."""
+        _ck(lib().ofhe_peer_barrier(self.h, flags_of_rank, len(flags_of_rank), rank, index, _stream()))
+
+    def peer_barrier_timeouts(self, flags_ptr, world, n_barriers):
+        n = C.c_uint64(0)
+        _ck(lib().ofhe_peer_barrier_timeouts(self.h, flags_ptr, world, n_barriers, C.byref(n)))
+        return n.value
 
 
 class Ring:
@@ -383,6 +436,27 @@ def shard_plan(sizeQ, sizeP, sizeQl, world, rank):
                 gather_p_row=lambda j, b: (((j + sizeQ) % world) * 2 + b) * (-(-sizeP // world)) + j // world)
 
 
+class PeerBuffers:
+    """The same raw buffer on every rank, addressable from this process: the local cudaMalloc allocation plus CUDA-IPC
+    mappings of the peers' (one process per GPU).  `exchange(obj) -> [obj of rank 0, ..., obj of rank world-1]` is the
+    caller's control-plane all-gather (torch.distributed.all_gather_object)."""
+
+    def __init__(self, ctx, words, rank, world, exchange):
+        self.ctx, self.rank, self.world, self.words = ctx, rank, world, int(words)
+        self.local = ctx.raw_zeros(max(self.words, 1))
+        handles = exchange(ctx.ipc_export(self.local))
+        self.ptrs = [self.local if r == rank else ctx.ipc_import(handles[r]) for r in range(world)]
+        self.array = ptr_array(self.ptrs)
+
+    def close(self):
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                self.ctx.ipc_release(p)
+        if self.local:
+            self.ctx.raw_free(self.local)
+        self.ptrs, self.local = [], None
+
+
 class Shard:
     """One rank's share of a limb-sharded CKKS EvalMult.  `all_gather(buf)` is supplied by the caller: in place on a
     [world, ...] tensor (torch.distributed.all_gather_into_tensor over NCCL in production; a local copy loop in the
@@ -421,6 +495,22 @@ class Shard:
 
     def phase_c(self, sizeQl, gather_p, out):
         _ck(lib().ofhe_shard_evalmult_c(self.h, sizeQl, _ptr(gather_p), _ptr(out), _stream()))
+
+    # ---- exchange by peer stores + device barrier (no collective call); gq/gp/flags: ptr_array() of every rank's buffer
+    def phase_a_push(self, sizeQl, ct1, ct2, out, gq_of_rank):
+        _ck(lib().ofhe_shard_evalmult_a_push(self.h, sizeQl, _ptr(ct1), _ptr(ct2), _ptr(out), gq_of_rank, _stream()))
+
+    def phase_b_push(self, sizeQl, evk_a, evk_b, gq_of_rank, gp_of_rank):
+        _ck(lib().ofhe_shard_evalmult_b_push(self.h, sizeQl, _ptr(evk_a), _ptr(evk_b), gq_of_rank, gp_of_rank,
+                                             _stream()))
+
+    def evalmult_push(self, sizeQl, ct1, ct2, evk_a, evk_b, out, gq_of_rank, gp_of_rank, flags_of_rank, slot=0):
+        ctx = self.ring.ctx
+        self.phase_a_push(sizeQl, ct1, ct2, out, gq_of_rank)
+        ctx.peer_barrier(flags_of_rank, self.rank, 2 * slot)
+        self.phase_b_push(sizeQl, evk_a, evk_b, gq_of_rank, gp_of_rank)
+        ctx.peer_barrier(flags_of_rank, self.rank, 2 * slot + 1)
+        self.phase_c(sizeQl, gp_of_rank[self.rank], out)
 
     def evalmult(self, sizeQl, ct1, ct2, evk_a, evk_b, out, gather_q, gather_p, all_gather):
         self.phase_a(sizeQl, ct1, ct2, out, gather_q)

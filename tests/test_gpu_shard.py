@@ -9,7 +9,7 @@ from oracle_lib import seeded_residues
 pytestmark = pytest.mark.gpu
 
 
-def run_virtual(m, ctx0, p, world, sizeQl, ct1, ct2, ea, eb):
+def run_virtual(m, ctx0, p, world, sizeQl, ct1, ct2, ea, eb, push=False):
     """Returns the full [2][sizeQl][N] result assembled from the ranks' local rows."""
     import torch
 
@@ -41,15 +41,33 @@ def run_virtual(m, ctx0, p, world, sizeQl, ct1, ct2, ea, eb):
                     ranks[dst][key][src].copy_(ranks[src][key][src])
         torch.cuda.synchronize()
 
-    for d in ranks:
-        d["sh"].phase_a(sizeQl, d["ct1"], d["ct2"], d["out"], d["gq"])
-    exchange("gq")
-    for d in ranks:
-        d["sh"].phase_b(sizeQl, d["gq"], d["ea"], d["eb"], d["gp"])
-    exchange("gp")
-    for d in ranks:
-        d["sh"].phase_c(sizeQl, d["gp"], d["out"])
-    torch.cuda.synchronize()
+    if push:
+        # exchange by peer stores + device barriers: every virtual rank on its own stream, no host synchronisation
+        # between the phases; run twice back to back on the same buffers (reuse safety)
+        nfl = m.lib().ofhe_peer_flags_words(world, 2)
+        flags = [ctx0.zeros(nfl) for _ in range(world)]
+        gq_arr = m.ptr_array([d["gq"] for d in ranks])
+        gp_arr = m.ptr_array([d["gp"] for d in ranks])
+        fl_arr = m.ptr_array(flags)
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        torch.cuda.synchronize()
+        for _ in range(2):
+            for r, d in enumerate(ranks):
+                with torch.cuda.stream(streams[r]):
+                    d["sh"].evalmult_push(sizeQl, d["ct1"], d["ct2"], d["ea"], d["eb"], d["out"], gq_arr, gp_arr, fl_arr)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert ctx0.peer_barrier_timeouts(flags[r].data_ptr(), world, 2) == 0, "device barrier timed out"
+    else:
+        for d in ranks:
+            d["sh"].phase_a(sizeQl, d["ct1"], d["ct2"], d["out"], d["gq"])
+        exchange("gq")
+        for d in ranks:
+            d["sh"].phase_b(sizeQl, d["gq"], d["ea"], d["eb"], d["gp"])
+        exchange("gp")
+        for d in ranks:
+            d["sh"].phase_c(sizeQl, d["gp"], d["out"])
+        torch.cuda.synchronize()
     full = np.zeros((2, sizeQl, N), dtype=np.uint64)
     for d in ranks:
         if d["own_q"]:
@@ -87,5 +105,8 @@ def test_virtual_ranks_match_unsharded(gpu, oracle, args, worlds):
         for world in worlds:
             got = run_virtual(m, ctx, p, world, sizeQl, ct1, ct2, ea, eb)
             assert (got == want).all(), f"world={world} sizeQl={sizeQl}"
+            if world > 1:
+                got = run_virtual(m, ctx, p, world, sizeQl, ct1, ct2, ea, eb, push=True)
+                assert (got == want).all(), f"peer-push world={world} sizeQl={sizeQl}"
     for o in (evk, hks, ring):
         o.close()

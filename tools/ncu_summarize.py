@@ -1,0 +1,45 @@
+"""Summarise an ncu report (.ncu-rep, read with `ncu -i ... --page raw --csv`) into a small CSV for profiles/.
+usage: python tools/ncu_summarize.py gpurun_out/x.ncu-rep > profiles/rNN_x_summary.csv
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "duration_us"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("launch__registers_per_thread", "regs"),
+    ("dram__bytes_read.sum", "dram_read"),
+    ("dram__bytes_write.sum", "dram_write"),
+    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "fmaheavy_pct"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu_pct"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math_throttle"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall_dispatch"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    out = csv.writer(sys.stdout)
+    out.writerow(["kernel"] + [f"{n}[{units[hdr.index(k)]}]" if k in hdr else n for k, n in KEYS])
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        name = d.get("Kernel Name", "?").split("(")[0].replace("void ", "").replace("ofhe::<unnamed>::", "")
+        out.writerow([name] + [d.get(k, "") for k, _ in KEYS])
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,29 @@ for sizeQl in (sizeQ, sizeQ - 1):
 
     sh.evalmult(sizeQl, d1, d2, a_d, b_d, out, gq, gp, all_gather)
     torch.cuda.synchronize()
+    # the same multiplication with the exchange done by peer stores + device barriers (no collective), twice in a row
+    # on the same buffers (buffer-reuse safety), must reproduce the NCCL result bit for bit
+    def exchange(obj):
+        objs = [None] * world
+        dist.all_gather_object(objs, obj)
+        return objs
+
+    pq = m.PeerBuffers(ctx, world * info["slots_q"] * N, rank, world, exchange)
+    pp = m.PeerBuffers(ctx, world * 2 * info["slots_p"] * N, rank, world, exchange)
+    pf = m.PeerBuffers(ctx, m.lib().ofhe_peer_flags_words(world, 2), rank, world, exchange)
+    dist.barrier()
+    out2 = ctx.zeros(2, len(own_q), N)
+    for _ in range(2):
+        sh.evalmult_push(sizeQl, d1, d2, a_d, b_d, out2, pq.array, pp.array, pf.array, slot=0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    timeouts = ctx.peer_barrier_timeouts(pf.local, world, 2)
+    push_same = bool((out2 == out).all()) and timeouts == 0
+    print(f"shard_check push world={world} rank={rank} sizeQl={sizeQl}: {'OK' if push_same else 'MISMATCH'}"
+          f" (barrier timeouts {timeouts})", flush=True)
+    ok = ok and push_same
+    for b in (pq, pp, pf):
+        b.close()
     # assemble on rank 0: pad every rank's rows to slots_q
     pad = ctx.zeros(2, info["slots_q"], N)
     pad[:, :len(own_q)] = out
@@ -66,7 +89,7 @@ for sizeQl in (sizeQ, sizeQ - 1):
         hks.close()
     sh.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
-dist.broadcast(flag, 0)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) == 1 else 1)
