@@ -368,6 +368,13 @@ def main():
     roofline = dict(bound="hbm", kernel="ntt_fwd (ntt_fwd_strided<4> + ntt_fwd_tile)", achieved=achieved, peak=peak,
                     unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
                     algorithmic_bytes_per_launch=ntt_bytes, us_per_limb_ntt=ntt_ms * 1e3 / L)
+    # the co-roof that actually binds a 60-bit NTT on sm_100: integer issue on the multiplier pipe,
+    # ~32 cycles per warp-butterfly (6 IMAD.WIDE + 4 IMAD + carries), 4 sub-partitions per SM
+    sm_mhz = (sampler.summary().get("sm_max_mhz") or 1965.0)
+    logn = N.bit_length() - 1
+    floor_us = (N // 2 * logn / 32.0) * 32.0 / (ctx.sm_count * 4) / sm_mhz
+    roofline["int_issue"] = dict(bound="integer multiplier issue (fmaheavy pipe)", cycles_per_warp_butterfly=32,
+                                 floor_us_per_limb_ntt=floor_us, frac=floor_us / (ntt_ms * 1e3 / L))
 
     line = None
     if rank == 0:

@@ -1,6 +1,6 @@
 """One EvalMult step at BASELINE config 2 bracketed by cudaProfilerStart/Stop, for ncu (--profile-from-start off).
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv \
-      python tools/profile_step.py [--op evalmult|ntt]
+      python tools/profile_step.py [--op evalmult|ntt|ntt240]
 """
 import argparse
 import os
@@ -30,11 +30,17 @@ ring.fill_uniform(ct2.view(2 * sizeQ, N), idx2, 12)
 slab = ctx.zeros(sizeQ + sizeP, N)
 lidx = list(range(sizeQ + sizeP))
 ring.fill_uniform(slab, lidx, 5)
+if a.op == "ntt240":  # exactly bench.py's roofline launch: forward NTT of a 240-limb slab (> L2)
+    slab = ctx.zeros(240, N)
+    lidx = [i % (sizeQ + sizeP) for i in range(240)]
+    ring.fill_uniform(slab, lidx, 99)
 
 
 def step():
     if a.op == "evalmult":
         hks.evalmult(sizeQ, ct1, ct2, evk, out)
+    elif a.op == "ntt240":
+        ring.ntt_fwd(slab, slab, lidx)
     else:
         ring.ntt_fwd(slab, slab, lidx)
         ring.ntt_inv(slab, slab, lidx)

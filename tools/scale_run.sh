@@ -1,10 +1,9 @@
-# round-end style scaling run on an N-GPU box: sharded-parity check at world 8/4, then bench at 8, 4, 2 (and 1)
+# scaling run on an 8-GPU box: sharded parity (NCCL + peer-push) at world 8 / 4, then bench.py at 8 and 4
 set -x
-NG=$(python -c "import torch; print(torch.cuda.device_count())")
 for W in 8 4; do
-  [ $W -le $NG ] && timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$W --master-addr 127.0.0.1 --master-port 29517 tools/shard_check.py 2>&1 | grep -E "OK|MISMATCH|Error|error" | head -12
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$W --master-addr 127.0.0.1 --master-port 29517 tools/shard_check.py 2>&1 | grep -E "OK|MISMATCH|Error|error|Traceback" | sort | uniq -c | head -20
 done
-for W in 8 4 2; do
-  [ $W -le $NG ] && timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$W --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $W --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/scale_$W.json
+for mode in "--gpus 8 --exchange push" "--gpus 8 --exchange push --no-graph" "--gpus 4 --exchange push"; do
+  W=$(echo $mode | cut -d' ' -f2)
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$W --master-addr 127.0.0.1 --master-port 29518 bench.py --steps 20 --warmup 3 $mode 2>&1 | tail -2 | cut -c1-900 | tee -a gpurun_out/scale_push.jsonl
 done
-timeout 400 python bench.py --gpus 1 --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/scale_1.json
