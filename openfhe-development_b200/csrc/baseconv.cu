@@ -6,20 +6,21 @@
 //     out_j = ( sum_i y_i * QHatModp[i][j] )  mod p_j               (128-bit accumulate + Barrett)
 // Results are the same canonical residues as the reference's Mul128 / BarrettUint128ModUint64 path.
 //
-// GPU formulation.  grid = (coefficient blocks, output groups, batch): a thread owns two coefficients and JPT = 8
-// target limbs (a 15 -> 45 conversion of 65536 coefficients runs on 6 x 32768 threads), and every 128-bit shared-memory
-// read of the conversion matrix feeds 16 IMADs.  The source
-// residues arrive already multiplied by QHatInvModq when the caller folded that constant into the last stage of the
-// inverse NTT (`premultiplied`), else the kernel does the Shoup multiply itself.  The 60x60-bit
-// multiply-accumulate works on 30-bit halves so that each MAC is exactly four IMAD.WIDE.U32 with NO carry chain
-// (the integer-FMA pipe issues at full rate on sm_100, the ALU pipe carrying IADD3 at half rate):
+// GPU formulation.  grid = (coefficient blocks, output groups, batch): a thread owns one coefficient and a group of
+// up to JPT = 16 target limbs (a 15 -> 45 conversion of 65536 coefficients runs on 3 x 65536 threads); the group loop
+// stays rolled, two outputs per iteration, and its trip count follows the real number of outputs, so the prologue
+// (16 source loads, the 30-bit split, the shared-memory fills: a third of the run time at JPT = 8 by ncu's sampling)
+// is amortised without padding waste.  Every 128-bit shared-memory read of the conversion matrix is a warp-wide
+// broadcast and feeds 8 IMAD.WIDE.  The source residues arrive already multiplied by QHatInvModq when the caller
+// folded that constant into the last stage of the inverse NTT (`premultiplied`), else the kernel does the Shoup
+// multiply itself.  The 60x60-bit multiply-accumulate works on 30-bit halves so that each MAC is exactly four
+// IMAD.WIDE.U32 with NO carry chain:
 //     y = y1*2^30 + y0,  m = m1*2^30 + m0   ->   c0 += y0*m0; c1a += y0*m1; c1b += y1*m0; c2 += y1*m1
-// Each partial sum stays below 2^64 for 16 terms.  The four column sums are then reduced WITHOUT assembling a
-// 128-bit value: S = c0 + (c1a + c1b) 2^30 + c2 2^60 (mod p) is formed from Shoup-lazy products with the constants
-// 2^30 mod p and 2^60 mod p (IMAD work again, instead of the shift / carry chains of a 128-bit Barrett reduction that
-// would make the half-rate ALU pipe the bottleneck).  The matrix slice of the CTA's output group is zero-padded in shared memory to 16*CH x JPT, so the
-// MAC loops have compile-time bounds and no predication.  Requires q_i, p_j < 2^60 (MAX_MODULUS_SIZE,
-// core/include/math/hal/basicint.h:48).
+// Each partial sum stays below 2^64 for 16 terms.  The four column sums are then assembled into one 128-bit integer
+// S = c0 + (c1a + c1b) 2^30 + c2 2^60 (shifts and adds only) and reduced by a single 128 -> 64 Barrett step per output
+// (~14 multiplier instructions; reducing the four columns separately with Shoup-lazy products took ~32).  The matrix
+// slice of the CTA's output group is zero-padded in shared memory to 16*CH x JPT, so the MAC loops have compile-time
+// bounds and no predication.  Requires q_i, p_j < 2^60 (MAX_MODULUS_SIZE, core/include/math/hal/basicint.h:48).
 #include <cstdlib>
 
 #include "internal.h"
@@ -29,7 +30,7 @@ namespace {
 
 constexpr uint32_t kMask30 = (1u << 30) - 1;
 #ifndef OFHE_BCONV_JPT
-#define OFHE_BCONV_JPT 8
+#define OFHE_BCONV_JPT 16
 #endif
 #ifndef OFHE_BCONV_MINB
 #define OFHE_BCONV_MINB 1
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
     constexpr int MAXQ = 16 * CH;
     __shared__ __align__(16) uint2 s_mat[MAXQ * kJPT];
     __shared__ uint64_t s_src[MAXQ * 3];  // q, w, ws
-    __shared__ uint64_t s_dst[kJPT * 6];  // p, 2^30 mod p (+Shoup), 2^60 mod p (+Shoup), floor(2^64/p)
+    __shared__ uint64_t s_dst[kJPT * 4];  // p, floor(2^128/p) hi, lo, (pad)
     in += blockIdx.z * in_stride;
     out += blockIdx.z * out_stride;
     const uint32_t j0 = blockIdx.y * kJPT;
@@ -94,10 +95,11 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
         s_src[3 * i + 2] = ok ? t.qhatinv[2 * i + 1] : 0;
     }
     if (threadIdx.x < kJPT) {
+        static_assert(kJPT <= kThreads, "one thread per target limb fills s_dst");
         const uint32_t j   = j0 + threadIdx.x < t.sizeP ? j0 + threadIdx.x : t.sizeP - 1;
         const ModConst& mc = r.mc[pmap.idx[j]];
-        uint64_t* d        = s_dst + 6 * threadIdx.x;
-        d[0] = mc.q, d[1] = mc.r30, d[2] = mc.r30s, d[3] = mc.r60, d[4] = mc.r60s, d[5] = mc.one_s;
+        uint64_t* d        = s_dst + 4 * threadIdx.x;
+        d[0] = mc.q, d[1] = mc.mu128_hi, d[2] = mc.mu128_lo, d[3] = mc.one_s;
     }
     __syncthreads();
 
@@ -124,9 +126,10 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
         }
     }
     // the output-pair loop stays rolled: the fully unrolled body (64 KB of code) thrashed the instruction cache
+    const int nj = min(kJPT, (int)((t.sizeP - j0 + 1u) & ~1u));  // outputs of this group, rounded up to a pair
 #pragma unroll 1
-    for (int j = 0; j < kJPT; j += 2) {
-        uint64_t total[kCPT][2];
+    for (int j = 0; j < nj; j += 2) {
+        unsigned __int128 total[kCPT][2];
 #pragma unroll
         for (int c = 0; c < kCPT; ++c)
             total[c][0] = total[c][1] = 0;
@@ -154,31 +157,27 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
                 }
             }
 #pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                const uint64_t* d = s_dst + 6 * (j + o);
-                const uint64_t np = 0 - d[0];
+            for (int o = 0; o < 2; ++o)
 #pragma unroll
                 for (int c = 0; c < kCPT; ++c) {
-                    // v = c0 + (c1a + c1b) 2^30 + c2 2^60 (mod p), below 8p: the four Shoup-lazy terms
-                    // c_k w_k - floor(c_k w_k' / 2^64) p share ONE multiplication by -p (everything is mod 2^64 and
-                    // the true value is below 2^63, so the wrapped sum is exact)
+                    // the four column sums go into ONE 128-bit integer (shifts and adds, no multiplier):
+                    // S = c0 + (c1a + c1b) 2^30 + c2 2^60 < 2^125 per chunk of 16 source limbs, CH <= 4 chunks
                     const uint64_t* a4 = a[c][o];
-                    const uint64_t h   = mulhi(a4[0], d[5]) + mulhi(a4[1], d[2]) + mulhi(a4[2], d[2]) + mulhi(a4[3], d[4]);
-                    const uint64_t v   = a4[0] + (a4[1] + a4[2]) * d[1] + a4[3] * d[3] + h * np;
-                    total[c][o] += CH == 1 ? v : lazy_reduce_n(v, d[5], np);  // CH <= 4 chunks: < 8p
+                    total[c][o] += (unsigned __int128)a4[0] + ((((unsigned __int128)a4[1]) + a4[2]) << 30) +
+                                   (((unsigned __int128)a4[3]) << 60);
                 }
-            }
         }
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-            const uint64_t* d = s_dst + 6 * (j + o);
+            const uint64_t* d = s_dst + 4 * (j + o);
 #pragma unroll
             for (int c = 0; c < kCPT; ++c) {
                 const uint32_t rr = rr0 + c * kThreads;
                 if (j0 + j + o < t.sizeP && rr < N) {
                     const uint32_t jj = j0 + j + o;
                     const uint64_t p  = d[0];
-                    uint64_t v        = csub(lazy_reduce_n(total[c][o], d[5], 0 - p), p);
+                    // one 128 -> 64 Barrett step per output (the reference's BarrettUint128ModUint64 value)
+                    uint64_t v = barrett128((uint64_t)(total[c][o] >> 64), (uint64_t)total[c][o], p, d[1], d[2]);
                     if (MODE == 1) {  // dcrtpoly-impl.h:1060,1073: minus alphaQModp[(size_t)nu][j]
                         const uint64_t a = t.alpha[(size_t)__double2ull_rz(nu[c]) * t.sizeP + jj];
                         v                = submod(v, a, p);
@@ -189,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
                         v                 = addmod(v, mulmod(xo, t.extra[jj], mc), p);
                         uint64_t a;
                         if (fabs(nu[c]) <= 9223372036854774784.0)  // isConvertableToNativeInt (utils/utilities.h:100-126)
-                            a = csub(lazy_reduce_n(__double2ull_rz(nu[c]), d[5], 0 - p), p);
+                            a = csub(lazy_reduce_n(__double2ull_rz(nu[c]), d[3], 0 - p), p);
                         else {
                             uint64_t hi, lo;
                             double_to_u128(nu[c], hi, lo);
