@@ -365,15 +365,19 @@ def main():
     peak, peak_src = measured_peak_gbs()
     ntt_bytes = 16.0 * N * L
     achieved = ntt_bytes / (ntt_ms * 1e-3) / 1e9
+    # DRAM bytes of exactly this launch (both kernels) from `ncu --set full` (profiles/r01f_ntt240_summary.csv:
+    # dram read + write = 125.9 + 67.7 + 325.3 + 94.8 MB): 2.4x the algorithmic bytes -- the per-tile twiddles (1 MiB per
+    # 0.5 MiB limb) and the intermediate between the two kernels
+    traffic = 613.6e6 if (N == 65536 and L == 240) else None
     roofline = dict(bound="hbm", kernel="ntt_fwd (ntt_fwd_strided<4> + ntt_fwd_tile)", achieved=achieved, peak=peak,
-                    unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=ntt_bytes, us_per_limb_ntt=ntt_ms * 1e3 / L)
     # the co-roof that actually binds a 60-bit NTT on sm_100: integer issue on the multiplier pipe,
-    # ~32 cycles per warp-butterfly (6 IMAD.WIDE + 4 IMAD + carries), 4 sub-partitions per SM
+    # ~41 cycles per warp-butterfly (6.2 IMAD.WIDE at 4 + ~8 IMAD-class at 2, ncu pipe accounting), 4 sub-partitions per SM
     sm_mhz = (sampler.summary().get("sm_max_mhz") or 1965.0)
     logn = N.bit_length() - 1
-    floor_us = (N // 2 * logn / 32.0) * 32.0 / (ctx.sm_count * 4) / sm_mhz
-    roofline["int_issue"] = dict(bound="integer multiplier issue (fmaheavy pipe)", cycles_per_warp_butterfly=32,
+    floor_us = (N // 2 * logn / 32.0) * 41.0 / (ctx.sm_count * 4) / sm_mhz
+    roofline["int_issue"] = dict(bound="integer multiplier issue (fmaheavy pipe)", cycles_per_warp_butterfly=41,
                                  floor_us_per_limb_ntt=floor_us, frac=floor_us / (ntt_ms * 1e3 / L))
 
     line = None
