@@ -173,6 +173,20 @@ int ofhe_ckks_rescale(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_d, uint
 int ofhe_ckks_rotate(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, const uint64_t* ct_d, const ofhe_evk* evk,
                      uint64_t* out_d, void* stream);
 uint32_t ofhe_find_automorphism_index(int32_t index, uint32_t m);
+/* ---- hoisted rotations: one ModUp shared by many rotations of the same ciphertext.
+ *      EvalFastRotationPrecompute (base-leveledshe.cpp:425-431)  = ofhe_hks_modup on c1 -> digits_d
+ *      EvalFastRotation           (base-leveledshe.cpp:433-463)  = ofhe_ckks_fast_rotation:  (auto_k(ba0 + c0), auto_k(ba1))
+ *      EvalFastRotationExt        (ckksrns-leveledshe.cpp:534-582) = ofhe_ckks_fast_rotation_ext: result stays in QlP,
+ *                                  out_ext_d [2][sizeQl+sizeP][N]; add_first adds c0 * (P mod q_i)
+ *      KeySwitchExt               (keyswitch-hybrid.cpp:217-243) = ofhe_hks_keyswitch_ext: [c_k * (P mod q_i) | 0]
+ *      KeySwitchDown              (keyswitch-hybrid.cpp:246-277) = ofhe_hks_approx_mod_down(..., n_polys = 2)
+ *      ct_d [2][sizeQl][N], digits_d [numPartQl][sizeQl+sizeP][N] (caller-owned), EVALUATION format throughout.       */
+int ofhe_ckks_fast_rotation(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, const uint64_t* ct_d, const uint64_t* digits_d,
+                            const ofhe_evk* evk, uint64_t* out_d, void* stream);
+int ofhe_ckks_fast_rotation_ext(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, int add_first, const uint64_t* ct_d,
+                                const uint64_t* digits_d, const ofhe_evk* evk, uint64_t* out_ext_d, void* stream);
+int ofhe_hks_keyswitch_ext(ofhe_hks* hks, uint32_t sizeQl, int add_first, const uint64_t* ct_d, uint64_t* out_ext_d,
+                           void* stream);
 
 /* ---- a20 (host helper, setup time) CKKS modulus chain + auxiliary primes with the reference's selection rules
  *      ParameterGenerationCKKSRNS::SinglePrimeModuliGen  pke/lib/scheme/ckksrns/ckksrns-parametergeneration.cpp:409-518

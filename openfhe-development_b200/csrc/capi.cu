@@ -652,6 +652,29 @@ int ofhe_ckks_rotate(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, const uint64_t*
         hks->h->rotate(sizeQl, k, ct_d, *evk->k, out_d, S(stream));
     });
 }
+int ofhe_ckks_fast_rotation(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, const uint64_t* ct_d, const uint64_t* digits_d,
+                            const ofhe_evk* evk, uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(hks->h->ring);
+        OFHE_REQUIRE((k & 1) && k < 2 * hks->h->ring->N, "automorphism index must be odd and below 2N");
+        hks->h->fast_rotation(sizeQl, k, ct_d, digits_d, *evk->k, out_d, S(stream));
+    });
+}
+int ofhe_ckks_fast_rotation_ext(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, int add_first, const uint64_t* ct_d,
+                                const uint64_t* digits_d, const ofhe_evk* evk, uint64_t* out_ext_d, void* stream) {
+    return guard([&] {
+        use(hks->h->ring);
+        OFHE_REQUIRE((k & 1) && k < 2 * hks->h->ring->N, "automorphism index must be odd and below 2N");
+        hks->h->fast_rotation_ext(sizeQl, k, add_first != 0, ct_d, digits_d, *evk->k, out_ext_d, S(stream));
+    });
+}
+int ofhe_hks_keyswitch_ext(ofhe_hks* hks, uint32_t sizeQl, int add_first, const uint64_t* ct_d, uint64_t* out_ext_d,
+                           void* stream) {
+    return guard([&] {
+        use(hks->h->ring);
+        hks->h->keyswitch_ext(sizeQl, add_first != 0, ct_d, out_ext_d, S(stream));
+    });
+}
 uint32_t ofhe_find_automorphism_index(int32_t index, uint32_t m) {
     // FindAutomorphismIndex2nComplex (core/lib/math/nbtheory2.cpp:243-262): 5^index mod m (5^-1 for negative index)
     if (index == 0)

@@ -86,6 +86,8 @@ Hks::Hks(Ring* r, uint32_t sizeQ_, uint32_t sizeP_, uint32_t dnum_) : ring(r), s
         uint64_t q  = r->moduli[i];
         PModq[i]    = hm::prod_mod(P, sizeP, -1, q);
         PInvModq[i] = sizeP ? hm::inv(PModq[i], q) : 1;
+        pmodq_sv.s[i]  = PModq[i];
+        pmodq_sv.ss[i] = hm::shoup_const(PModq[i], q);
     }
 }
 Hks::~Hks() = default;
@@ -331,6 +333,49 @@ void Hks::rotate(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const EvalKey&
     const uint32_t* map = ring_automap(ring, k, st);
     launch_automorphism(r, out, tmp, map, 2 * sizeQl, st);
     (void)lv;
+}
+
+// EvalFastRotation (base-leveledshe.cpp:433-463): ba = EvalFastKeySwitchCore(digits, key_k) = inner product + ModDown,
+// out = (auto_k(ba0 + c0), auto_k(ba1)).  The ModUp that produced `digits` is shared by all rotations of the ciphertext.
+void Hks::fast_rotation(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const uint64_t* digits, const EvalKey& evk,
+                        uint64_t* out, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, P = (size_t)sizeQl * N, E = (size_t)(sizeQl + sizeP) * N;
+    uint64_t* ws    = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * (2 * E + 2 * sizeP * N + 4 * P)));
+    uint64_t* e01   = ws;
+    uint64_t* p_tmp = e01 + 2 * E;
+    uint64_t* conv  = p_tmp + 2 * (size_t)sizeP * N;
+    uint64_t* tmp   = conv + 2 * P;
+    OFHE_CUDA(cudaMemcpyAsync(tmp, ct, sizeof(uint64_t) * P, cudaMemcpyDeviceToDevice, st));  // addend (c0, 0)
+    OFHE_CUDA(cudaMemsetAsync(tmp + P, 0, sizeof(uint64_t) * P, st));
+    inner_product(sizeQl, lv.n_digits, digits, evk, e01, st);                                 // keyswitch-hybrid.cpp:402-435
+    mod_down2(sizeQl, e01, tmp, tmp, p_tmp, conv, st);                                        // :389-399
+    launch_automorphism(r, out, tmp, ring_automap(ring, k, st), 2 * sizeQl, st);              // base-leveledshe.cpp:455-457
+}
+
+// EvalFastRotationExt (ckksrns-leveledshe.cpp:534-582): cTilda = EvalFastKeySwitchCoreExt(digits, key_k) stays in QlP;
+// addFirst adds [c0 * (P mod q_i) | 0] to cTilda0; both polynomials through auto_k on all sizeQl + sizeP limbs.
+void Hks::fast_rotation_ext(uint32_t sizeQl, uint32_t k, bool add_first, const uint64_t* ct, const uint64_t* digits,
+                            const EvalKey& evk, uint64_t* out_ext, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, E = (size_t)(sizeQl + sizeP) * N;
+    uint64_t* e01  = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * 2 * E));
+    inner_product(sizeQl, lv.n_digits, digits, evk, e01, st);
+    if (add_first)  // :561-570
+        launch_mul_scalars_add(r, e01, ct, pmodq_sv, e01, lv.map_Ql, st);
+    launch_automorphism(r, out_ext, e01, ring_automap(ring, k, st), 2 * (sizeQl + sizeP), st);  // :576-577
+}
+
+// KeySwitchExt (keyswitch-hybrid.cpp:217-243): lift to QlP as [c_k * (P mod q_i) | 0]; c_0 only if addFirst
+void Hks::keyswitch_ext(uint32_t sizeQl, bool add_first, const uint64_t* ct, uint64_t* out_ext, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, P = (size_t)sizeQl * N, E = (size_t)(sizeQl + sizeP) * N;
+    OFHE_CUDA(cudaMemsetAsync(out_ext, 0, sizeof(uint64_t) * 2 * E, st));
+    for (uint32_t b = add_first ? 0 : 1; b < 2; ++b)
+        launch_mul_scalars(r, out_ext + b * E, ct + b * P, pmodq_sv, lv.map_Ql, st);
 }
 
 EvalKey::~EvalKey() {

@@ -61,6 +61,14 @@ struct Hks {
                   cudaStream_t st);
     void rescale(uint32_t sizeQl, const uint64_t* in, uint64_t* out, uint32_t n_polys, cudaStream_t st);
     void rotate(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const EvalKey& evk, uint64_t* out, cudaStream_t st);
+    // hoisted rotations: digits = modup(c1) computed ONCE by the caller and shared by several rotations
+    void fast_rotation(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const uint64_t* digits, const EvalKey& evk,
+                       uint64_t* out, cudaStream_t st);
+    // result stays in the extended basis QlP: out_ext [2][sizeQl+sizeP][N]
+    void fast_rotation_ext(uint32_t sizeQl, uint32_t k, bool add_first, const uint64_t* ct, const uint64_t* digits,
+                           const EvalKey& evk, uint64_t* out_ext, cudaStream_t st);
+    void keyswitch_ext(uint32_t sizeQl, bool add_first, const uint64_t* ct, uint64_t* out_ext, cudaStream_t st);
+    ScalarVec pmodq_sv;  // P mod q_i with Shoup constants (GetPModq, rns-cryptoparameters.h)
 };
 
 }  // namespace ofhe

@@ -63,6 +63,9 @@ SIGNATURES = {
     "ofhe_ckks_evalmult_host_batch": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_ckks_rescale": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp]),
     "ofhe_ckks_rotate": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_fast_rotation": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_fast_rotation_ext": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_hks_keyswitch_ext": (C.c_int, [_vp, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "ofhe_find_automorphism_index": (C.c_uint32, [C.c_int32, C.c_uint32]),
     "ofhe_ckks_paramgen": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp,
                                       _vp]),
@@ -421,6 +424,20 @@ class Hks:
 
     def rotate(self, sizeQl, k, ct, evk, out):
         _ck(lib().ofhe_ckks_rotate(self.h, sizeQl, k, _ptr(ct), evk.h, _ptr(out), _stream()))
+
+    # hoisted rotations: digits = modup(ct[1]) once (EvalFastRotationPrecompute), then any number of rotations
+    def fast_rotation(self, sizeQl, k, ct, digits, evk, out):
+        _ck(lib().ofhe_ckks_fast_rotation(self.h, sizeQl, k, _ptr(ct), _ptr(digits), evk.h, _ptr(out), _stream()))
+
+    def fast_rotation_ext(self, sizeQl, k, add_first, ct, digits, evk, out_ext):
+        _ck(lib().ofhe_ckks_fast_rotation_ext(self.h, sizeQl, k, int(add_first), _ptr(ct), _ptr(digits), evk.h,
+                                              _ptr(out_ext), _stream()))
+
+    def keyswitch_ext(self, sizeQl, add_first, ct, out_ext):
+        _ck(lib().ofhe_hks_keyswitch_ext(self.h, sizeQl, int(add_first), _ptr(ct), _ptr(out_ext), _stream()))
+
+    def keyswitch_down(self, sizeQl, ct_ext, out):
+        self.approx_mod_down(sizeQl, ct_ext, out, n_polys=2)
 
 
 # ---- limb-sharded EvalMult (SURVEY.md 8 e) --------------------------------------------------------------------------

@@ -836,6 +836,81 @@ void orc_ckks_automorphism_ct(const orc_ckks* c, uint32_t sizeQl, uint32_t k, co
 }
 
 
+/* ------------------------------------------------------------------ hoisted rotations
+ * EvalFastRotation (base-leveledshe.cpp:433-463): with digits = EvalKeySwitchPrecomputeCore(c1) computed ONCE for
+ * several rotations, ba = EvalFastKeySwitchCore(digits, key_k) (inner product + ModDown), out = (auto_k(ba0 + c0),
+ * auto_k(ba1)).  digits: [numPartQl][sizeQl+sizeP][N] from orc_ckks_modup.                                       */
+void orc_ckks_fast_rotation(const orc_ckks* c, uint32_t sizeQl, uint32_t k, const uint64_t* ct, const uint64_t* digits,
+                            const uint64_t* evk_a, const uint64_t* evk_b, uint64_t* out) {
+    uint32_t N = c->N, sizeQlP = sizeQl + c->sizeP;
+    uint32_t numPart = (sizeQl + c->alpha - 1) / c->alpha;
+    if (numPart > c->dnum)
+        numPart = c->dnum;
+    size_t P = (size_t)sizeQl * N, E = (size_t)sizeQlP * N;
+    uint64_t* e   = (uint64_t*)malloc(sizeof(uint64_t) * 2 * E);
+    uint64_t* ba  = (uint64_t*)malloc(sizeof(uint64_t) * 2 * P);
+    uint32_t* map = (uint32_t*)malloc(sizeof(uint32_t) * N);
+    orc_ckks_inner_product(c, sizeQl, numPart, digits, evk_a, evk_b, e, e + E);
+    orc_ckks_approx_mod_down(c, sizeQl, e, ba);
+    orc_ckks_approx_mod_down(c, sizeQl, e + E, ba + P);
+    orc_automorphism_map(N, k, map);
+    for (uint32_t i = 0; i < sizeQl; ++i) {
+        size_t o = (size_t)i * N;
+        orc_limb_binop(c->q[i], N, 0, ba + o, ct + o, ba + o);
+        orc_automorphism_eval(N, map, ba + o, out + o);
+        orc_automorphism_eval(N, map, ba + P + o, out + P + o);
+    }
+    free(e), free(ba), free(map);
+}
+/* EvalFastRotationExt (ckksrns-leveledshe.cpp:534-582): the result STAYS in the extended basis QlP:
+ * cTilda = EvalFastKeySwitchCoreExt(digits, key_k); if addFirst, cTilda0 += [c0 * (P mod q_i) | 0]; both polys through
+ * auto_k on all sizeQl + sizeP limbs.  out: [2][sizeQl+sizeP][N].                                                */
+void orc_ckks_fast_rotation_ext(const orc_ckks* c, uint32_t sizeQl, uint32_t k, int add_first, const uint64_t* ct,
+                                const uint64_t* digits, const uint64_t* evk_a, const uint64_t* evk_b, uint64_t* out) {
+    uint32_t N = c->N, sizeQlP = sizeQl + c->sizeP;
+    uint32_t numPart = (sizeQl + c->alpha - 1) / c->alpha;
+    if (numPart > c->dnum)
+        numPart = c->dnum;
+    size_t E = (size_t)sizeQlP * N;
+    uint64_t* e    = (uint64_t*)malloc(sizeof(uint64_t) * 2 * E);
+    uint64_t* tmp  = (uint64_t*)malloc(sizeof(uint64_t) * N);
+    uint64_t* pmod = (uint64_t*)malloc(sizeof(uint64_t) * c->sizeQ);
+    uint32_t* map  = (uint32_t*)malloc(sizeof(uint32_t) * N);
+    orc_ckks_inner_product(c, sizeQl, numPart, digits, evk_a, evk_b, e, e + E);
+    orc_ckks_PModq(c, pmod);
+    if (add_first)
+        for (uint32_t i = 0; i < sizeQl; ++i) {
+            size_t o = (size_t)i * N;
+            orc_limb_mul_scalar(c->q[i], N, ct + o, pmod[i], tmp);
+            orc_limb_binop(c->q[i], N, 0, e + o, tmp, e + o);
+        }
+    orc_automorphism_map(N, k, map);
+    for (uint32_t b = 0; b < 2; ++b)
+        for (uint32_t i = 0; i < sizeQlP; ++i)
+            orc_automorphism_eval(N, map, e + b * E + (size_t)i * N, out + b * E + (size_t)i * N);
+    free(e), free(tmp), free(pmod), free(map);
+}
+/* KeySwitchExt (keyswitch-hybrid.cpp:217-243): lift a ciphertext to QlP: [c_k * (P mod q_i) | 0], c_0 only if addFirst */
+void orc_ckks_keyswitch_ext(const orc_ckks* c, uint32_t sizeQl, int add_first, const uint64_t* ct, uint64_t* out) {
+    uint32_t N = c->N, sizeQlP = sizeQl + c->sizeP;
+    size_t E = (size_t)sizeQlP * N;
+    uint64_t* pmod = (uint64_t*)malloc(sizeof(uint64_t) * c->sizeQ);
+    orc_ckks_PModq(c, pmod);
+    memset(out, 0, sizeof(uint64_t) * 2 * E);
+    for (uint32_t b = 0; b < 2; ++b)
+        if (add_first || b > 0)
+            for (uint32_t i = 0; i < sizeQl; ++i)
+                orc_limb_mul_scalar(c->q[i], N, ct + ((size_t)b * sizeQl + i) * N, pmod[i], out + b * E + (size_t)i * N);
+    free(pmod);
+}
+/* KeySwitchDown (keyswitch-hybrid.cpp:246-277): ApproxModDown of both polynomials of an extended ciphertext */
+void orc_ckks_keyswitch_down(const orc_ckks* c, uint32_t sizeQl, const uint64_t* ct_ext, uint64_t* out) {
+    size_t E = (size_t)(sizeQl + c->sizeP) * c->N, P = (size_t)sizeQl * c->N;
+    orc_ckks_approx_mod_down(c, sizeQl, ct_ext, out);
+    orc_ckks_approx_mod_down(c, sizeQl, ct_ext + E, out + P);
+}
+
+
 /* ------------------------------------------------------------------ a12: exact SwitchCRTBasis (BFV, HPS)
  * dcrtpoly-impl.h:1046-1084: as a10 plus the overflow count  nu = 0.5 + sum_i double(y_i) * qInv[i]  (IEEE double,
  * one multiply then one add per term, in index order, NO fused multiply-add), alpha = (size_t)nu, and

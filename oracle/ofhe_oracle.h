@@ -89,6 +89,14 @@ void orc_ckks_rescale_poly(const orc_ckks* c, uint32_t sizeQl, const uint64_t* x
 void orc_ckks_automorphism_ct(const orc_ckks* c, uint32_t sizeQl, uint32_t k, const uint64_t* ct,
                               const uint64_t* evk_a, const uint64_t* evk_b, uint64_t* out);
 
+/* hoisted rotations: digits from orc_ckks_modup(c1); *_ext results are [2][sizeQl+sizeP][N] */
+void orc_ckks_fast_rotation(const orc_ckks* c, uint32_t sizeQl, uint32_t k, const uint64_t* ct, const uint64_t* digits,
+                            const uint64_t* evk_a, const uint64_t* evk_b, uint64_t* out);
+void orc_ckks_fast_rotation_ext(const orc_ckks* c, uint32_t sizeQl, uint32_t k, int add_first, const uint64_t* ct,
+                                const uint64_t* digits, const uint64_t* evk_a, const uint64_t* evk_b, uint64_t* out);
+void orc_ckks_keyswitch_ext(const orc_ckks* c, uint32_t sizeQl, int add_first, const uint64_t* ct, uint64_t* out);
+void orc_ckks_keyswitch_down(const orc_ckks* c, uint32_t sizeQl, const uint64_t* ct_ext, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -578,6 +578,55 @@ int ref_ckks_rotate(void* hv, uint32_t sizeQl, int32_t index, const uint64_t* ct
         dump_poly(c->GetElements()[1], out + (size_t)sizeQl * h->N);
     });
 }
+// ---- hoisted rotations: EvalFastRotationPrecompute + EvalFastRotation / EvalFastRotationExt /
+// KeySwitchExt / KeySwitchDown on caller-supplied residues (rotation key of `index` must exist: ref_ckks_rotate_key)
+// cc->EvalFastRotation(ct, index, M, cc->EvalFastRotationPrecompute(ct)): [2][sizeQl][N] -> same shape
+int ref_ckks_fast_rotate(void* hv, uint32_t sizeQl, int32_t index, const uint64_t* ct, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a      = make_ct(h, sizeQl, ct, 2);
+        auto digits = h->cc->EvalFastRotationPrecompute(a);
+        auto c      = h->cc->EvalFastRotation(a, index, 2 * h->N, digits);
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)sizeQl * h->N);
+    });
+}
+// cc->EvalFastRotationExt(ct, index, digits, addFirst): [2][sizeQl][N] -> [2][sizeQl+sizeP][N] (extended basis QlP)
+int ref_ckks_fast_rotate_ext(void* hv, uint32_t sizeQl, int32_t index, int add_first, const uint64_t* ct,
+                             uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a      = make_ct(h, sizeQl, ct, 2);
+        auto digits = h->cc->EvalFastRotationPrecompute(a);
+        auto c      = h->cc->EvalFastRotationExt(a, index, digits, add_first != 0);
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)(sizeQl + h->sizeP) * h->N);
+    });
+}
+// cc->KeySwitchExt(ct, addFirst): [2][sizeQl][N] -> [2][sizeQl+sizeP][N]
+int ref_ckks_keyswitch_ext(void* hv, uint32_t sizeQl, int add_first, const uint64_t* ct, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a = make_ct(h, sizeQl, ct, 2);
+        auto c = h->cc->KeySwitchExt(a, add_first != 0);
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)(sizeQl + h->sizeP) * h->N);
+    });
+}
+// cc->KeySwitchDown on an extended ciphertext: [2][sizeQl+sizeP][N] -> [2][sizeQl][N]
+int ref_ckks_keyswitch_down(void* hv, uint32_t sizeQl, const uint64_t* ct_ext, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto a = make_ct(h, sizeQl, ct_ext, 2);  // template for metadata
+        auto e = h->cc->KeySwitchExt(a, true);   // right shape / params; towers overwritten below
+        auto& ev = e->GetElements();
+        for (uint32_t k = 0; k < 2; ++k)
+            ev[k] = make_poly(ev[k].GetParams(), Format::EVALUATION, ct_ext + (size_t)k * (sizeQl + h->sizeP) * h->N);
+        auto c = h->cc->KeySwitchDown(e);
+        dump_poly(c->GetElements()[0], out);
+        dump_poly(c->GetElements()[1], out + (size_t)sizeQl * h->N);
+    });
+}
 // honest end-to-end check material: encrypt a real vector, return its towers; decrypt towers back.
 int ref_ckks_encrypt(void* hv, const double* vals, uint32_t n, uint64_t* out) {
     auto* h = static_cast<CkksCtx*>(hv);

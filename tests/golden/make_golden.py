@@ -73,6 +73,13 @@ def main():
         g["rot_k"], g["rot_a"], g["rot_b"] = np.array([k]), ra, rb
         sizeQl = c.sizeQ - 1
         g["rot_out"] = c.rotate(sizeQl, 1, g[f"l{sizeQl}_ct1"])
+        # hoisted rotations: EvalFastRotation / EvalFastRotationExt / KeySwitchExt / KeySwitchDown
+        g["rot_fast"] = c.fast_rotate(sizeQl, 1, g[f"l{sizeQl}_ct1"])
+        g["rot_ext1"] = c.fast_rotate_ext(sizeQl, 1, True, g[f"l{sizeQl}_ct1"])
+        g["rot_ext0"] = c.fast_rotate_ext(sizeQl, 1, False, g[f"l{sizeQl}_ct1"])
+        g["ks_ext1"] = c.keyswitch_ext(sizeQl, True, g[f"l{sizeQl}_ct1"])
+        g["ks_ext0"] = c.keyswitch_ext(sizeQl, False, g[f"l{sizeQl}_ct1"])
+        g["ks_down"] = c.keyswitch_down(sizeQl, g["rot_ext1"])
         # an honest encryption / multiplication / decryption, for the end-to-end sanity test
         vals1 = np.array([0.5, -0.25, 1.0, 0.125])
         vals2 = np.array([2.0, 4.0, -1.0, 8.0])

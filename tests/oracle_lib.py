@@ -107,6 +107,11 @@ class Oracle:
         _sig(L, "orc_ckks_evalmult", None, C.c_void_p, C.c_uint32, u64p, u64p, u64p, u64p, u64p)
         _sig(L, "orc_ckks_rescale_poly", None, C.c_void_p, C.c_uint32, u64p, u64p)
         _sig(L, "orc_ckks_automorphism_ct", None, C.c_void_p, C.c_uint32, C.c_uint32, u64p, u64p, u64p, u64p)
+        _sig(L, "orc_ckks_fast_rotation", None, C.c_void_p, C.c_uint32, C.c_uint32, u64p, u64p, u64p, u64p, u64p)
+        _sig(L, "orc_ckks_fast_rotation_ext", None, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, u64p, u64p, u64p, u64p,
+             u64p)
+        _sig(L, "orc_ckks_keyswitch_ext", None, C.c_void_p, C.c_uint32, C.c_int, u64p, u64p)
+        _sig(L, "orc_ckks_keyswitch_down", None, C.c_void_p, C.c_uint32, u64p, u64p)
 
     # --- scalar / number theory -------------------------------------------------------------
     def barrett128(self, hi, lo, q):
@@ -307,6 +312,29 @@ class OracleCkks(_CkksCommon):
         self.L.orc_ckks_automorphism_ct(self.h, sizeQl, k, np.ascontiguousarray(ct), evk_a, evk_b, out)
         return out
 
+    # hoisted rotations: digits = self.modup(sizeQl, ct[1])
+    def fast_rotation(self, sizeQl, k, ct, digits, evk_a, evk_b):
+        out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
+        self.L.orc_ckks_fast_rotation(self.h, sizeQl, k, np.ascontiguousarray(ct), np.ascontiguousarray(digits), evk_a,
+                                      evk_b, out)
+        return out
+
+    def fast_rotation_ext(self, sizeQl, k, add_first, ct, digits, evk_a, evk_b):
+        out = np.empty((2, sizeQl + self.sizeP, self.N), dtype=np.uint64)
+        self.L.orc_ckks_fast_rotation_ext(self.h, sizeQl, k, int(add_first), np.ascontiguousarray(ct),
+                                          np.ascontiguousarray(digits), evk_a, evk_b, out)
+        return out
+
+    def keyswitch_ext(self, sizeQl, add_first, ct):
+        out = np.empty((2, sizeQl + self.sizeP, self.N), dtype=np.uint64)
+        self.L.orc_ckks_keyswitch_ext(self.h, sizeQl, int(add_first), np.ascontiguousarray(ct), out)
+        return out
+
+    def keyswitch_down(self, sizeQl, ct_ext):
+        out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
+        self.L.orc_ckks_keyswitch_down(self.h, sizeQl, np.ascontiguousarray(ct_ext), out)
+        return out
+
 
 class Reference:
     """The unmodified reference behind oracle/ref_shim.cpp."""
@@ -358,6 +386,10 @@ class Reference:
         _sig(L, "ref_ckks_time_evalmult", C.c_double, C.c_void_p, C.c_uint32, u64p, u64p, C.c_int, C.c_int)
         _sig(L, "ref_ckks_rescale", C.c_int, C.c_void_p, C.c_uint32, u64p, u64p)
         _sig(L, "ref_ckks_rotate", C.c_int, C.c_void_p, C.c_uint32, C.c_int32, u64p, u64p)
+        _sig(L, "ref_ckks_fast_rotate", C.c_int, C.c_void_p, C.c_uint32, C.c_int32, u64p, u64p)
+        _sig(L, "ref_ckks_fast_rotate_ext", C.c_int, C.c_void_p, C.c_uint32, C.c_int32, C.c_int, u64p, u64p)
+        _sig(L, "ref_ckks_keyswitch_ext", C.c_int, C.c_void_p, C.c_uint32, C.c_int, u64p, u64p)
+        _sig(L, "ref_ckks_keyswitch_down", C.c_int, C.c_void_p, C.c_uint32, u64p, u64p)
         _sig(L, "ref_bfv_create", C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32)
         _sig(L, "ref_bfv_destroy", None, C.c_void_p)
         _sig(L, "ref_bfv_shape", None, C.c_void_p, u32p, C.c_void_p, C.c_void_p)
@@ -554,6 +586,26 @@ class ReferenceCkks(_CkksCommon):
     def rotate(self, sizeQl, index, ct):
         out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
         self.r._ok(self.L.ref_ckks_rotate(self.h, sizeQl, index, np.ascontiguousarray(ct), out))
+        return out
+
+    def fast_rotate(self, sizeQl, index, ct):
+        out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_ckks_fast_rotate(self.h, sizeQl, index, np.ascontiguousarray(ct), out))
+        return out
+
+    def fast_rotate_ext(self, sizeQl, index, add_first, ct):
+        out = np.empty((2, sizeQl + self.sizeP, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_ckks_fast_rotate_ext(self.h, sizeQl, index, int(add_first), np.ascontiguousarray(ct), out))
+        return out
+
+    def keyswitch_ext(self, sizeQl, add_first, ct):
+        out = np.empty((2, sizeQl + self.sizeP, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_ckks_keyswitch_ext(self.h, sizeQl, int(add_first), np.ascontiguousarray(ct), out))
+        return out
+
+    def keyswitch_down(self, sizeQl, ct_ext):
+        out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_ckks_keyswitch_down(self.h, sizeQl, np.ascontiguousarray(ct_ext), out))
         return out
 
     def encrypt(self, vals):

@@ -263,6 +263,20 @@ def test_hybrid_keyswitch_golden(gpu, golden, name):
     out = ctx.zeros(2, sizeQl, N)
     hks.rotate(sizeQl, k, ctx.upload(g[f"l{sizeQl}_ct1"]), rk, out)
     assert (ctx.download(out) == g["rot_out"]).all()
+    # hoisted rotations against the reference's EvalFastRotation / EvalFastRotationExt / KeySwitchExt / KeySwitchDown
+    dct = ctx.upload(g[f"l{sizeQl}_ct1"])
+    digits = ctx.zeros(hks.num_digits(sizeQl), sizeQl + sizeP, N)
+    hks.modup(sizeQl, dct[1], digits)
+    hks.fast_rotation(sizeQl, k, dct, digits, rk, out)
+    assert (ctx.download(out) == g["rot_fast"]).all()
+    ext = ctx.zeros(2, sizeQl + sizeP, N)
+    for add_first in (True, False):
+        hks.fast_rotation_ext(sizeQl, k, add_first, dct, digits, rk, ext)
+        assert (ctx.download(ext) == g["rot_ext1" if add_first else "rot_ext0"]).all()
+        hks.keyswitch_ext(sizeQl, add_first, dct, ext)
+        assert (ctx.download(ext) == g["ks_ext1" if add_first else "ks_ext0"]).all()
+    hks.keyswitch_down(sizeQl, ctx.upload(g["rot_ext1"]), out)
+    assert (ctx.download(out) == g["ks_down"]).all()
     # honest ciphertexts from the reference: the device product is the ciphertext the reference decrypts correctly
     out = ctx.zeros(2, sizeQ, N)
     hks.evalmult(sizeQ, ctx.upload(g["enc1"]), ctx.upload(g["enc2"]), evk, out)
@@ -314,6 +328,22 @@ def test_hybrid_keyswitch_vs_oracle(gpu, oracle, args):
             out = ctx.zeros(2, sizeQl, N)
             hks.rotate(sizeQl, k, ctx.upload(ct1), evk, out)
             assert (ctx.download(out) == c.automorphism_ct(sizeQl, k, ct1, ea, eb)).all()
+            # hoisted: one ModUp, several rotations (here the same key stands in for every rotation key)
+            dct = ctx.upload(ct1)
+            hks.modup(sizeQl, dct[1], digits)
+            hd = ctx.download(digits)
+            ext = ctx.zeros(2, sizeQl + c.sizeP, N)
+            for idx in (3, -1):
+                kk = m.find_automorphism_index(idx, 2 * N)
+                hks.fast_rotation(sizeQl, kk, dct, digits, evk, out)
+                assert (ctx.download(out) == c.fast_rotation(sizeQl, kk, ct1, hd, ea, eb)).all(), f"fast rot {idx}"
+                hks.fast_rotation_ext(sizeQl, kk, idx == 3, dct, digits, evk, ext)
+                want_ext = c.fast_rotation_ext(sizeQl, kk, idx == 3, ct1, hd, ea, eb)
+                assert (ctx.download(ext) == want_ext).all(), f"fast rot ext {idx}"
+            hks.keyswitch_down(sizeQl, ext, out)
+            assert (ctx.download(out) == c.keyswitch_down(sizeQl, want_ext)).all()
+            hks.keyswitch_ext(sizeQl, True, dct, ext)
+            assert (ctx.download(ext) == c.keyswitch_ext(sizeQl, True, ct1)).all()
         for o in (evk, hks, ring):
             o.close()
     finally:
@@ -409,6 +439,25 @@ def test_config2_full_size(gpu, oracle):
         out2 = ctx.zeros(2, sizeQl - 1, N)
         hks.evalmult(sizeQl - 1, r, r, evk, out2)
         assert (ctx.download(out2) == c.evalmult(sizeQl - 1, hr, hr, ea, eb)).all()
+        # hoisting at full size (size-independent property): the hoisted rotation equals the plain one bit for bit.
+        # (KeySwitchDown of the extended-basis rotation is NOT bit-identical to it: the approximate base conversion
+        # does not commute with the sign flips of the automorphism; that path is pinned at the oracle's sizes.)
+        k = m.find_automorphism_index(5, 2 * N)
+        rot, fast = ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N)
+        hks.rotate(sizeQl, k, d1, evk, rot)
+        digits = ctx.zeros(hks.num_digits(sizeQl), sizeQl + c.sizeP, N)
+        hks.modup(sizeQl, d1[1], digits)
+        hks.fast_rotation(sizeQl, k, d1, digits, evk, fast)
+        assert bool((rot == fast).all())
+        ext, ext2 = ctx.zeros(2, sizeQl + c.sizeP, N), ctx.zeros(2, sizeQl + c.sizeP, N)
+        hks.fast_rotation_ext(sizeQl, k, True, d1, digits, evk, ext)
+        hks.fast_rotation_ext(sizeQl, k, False, d1, digits, evk, ext2)
+        lift = ctx.zeros(2, sizeQl + c.sizeP, N)
+        hks.keyswitch_ext(sizeQl, True, d1, lift)
+        # addFirst only adds auto_k(c0 * P mod q_i) to the Q limbs of the first polynomial
+        assert bool((ext[1] == ext2[1]).all()) and bool((ext[0, sizeQl:] == ext2[0, sizeQl:]).all())
+        assert bool((lift[:, sizeQl:] == 0).all())
+        del digits, ext, ext2, lift
         for o in (evk, hks, ring):
             o.close()
     finally:

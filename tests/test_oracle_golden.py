@@ -103,6 +103,14 @@ def test_ckks_golden(oracle, golden, name):
         sizeQl = c.sizeQ - 1
         out = c.automorphism_ct(sizeQl, int(g["rot_k"][0]), g[f"l{sizeQl}_ct1"], g["rot_a"], g["rot_b"])
         assert (out == g["rot_out"]).all()
+        ct, k, ra, rb = g[f"l{sizeQl}_ct1"], int(g["rot_k"][0]), g["rot_a"], g["rot_b"]
+        digits = c.modup(sizeQl, ct[1])
+        assert (c.fast_rotation(sizeQl, k, ct, digits, ra, rb) == g["rot_fast"]).all()
+        assert (c.fast_rotation_ext(sizeQl, k, True, ct, digits, ra, rb) == g["rot_ext1"]).all()
+        assert (c.fast_rotation_ext(sizeQl, k, False, ct, digits, ra, rb) == g["rot_ext0"]).all()
+        assert (c.keyswitch_ext(sizeQl, True, ct) == g["ks_ext1"]).all()
+        assert (c.keyswitch_ext(sizeQl, False, ct) == g["ks_ext0"]).all()
+        assert (c.keyswitch_down(sizeQl, g["rot_ext1"]) == g["ks_down"]).all()
         # honest ciphertexts: the oracle's EvalMult reproduces the reference's product ciphertext, which the
         # reference decrypts to the slot-wise product (within CKKS noise)
         assert (c.evalmult(c.sizeQ, g["enc1"], g["enc2"], ea, eb) == g["enc_prod"]).all()

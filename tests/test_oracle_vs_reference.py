@@ -112,6 +112,16 @@ def test_ckks_tables_and_keyswitch(oracle, reference, args):
             sizeQl = oc.sizeQ
             ct = np.stack([seeded_residues(21, oc.moduli[:sizeQl], N), seeded_residues(22, oc.moduli[:sizeQl], N)])
             assert (oc.automorphism_ct(sizeQl, k, ct, ra, rb) == rc.rotate(sizeQl, index, ct)).all()
+            # hoisted rotations: EvalFastRotation / EvalFastRotationExt / KeySwitchExt / KeySwitchDown
+            for lvl in sorted({sizeQl, max(1, sizeQl - 1)}, reverse=True):
+                cl = np.ascontiguousarray(ct[:, :lvl])
+                digits = oc.modup(lvl, cl[1])
+                assert (oc.fast_rotation(lvl, k, cl, digits, ra, rb) == rc.fast_rotate(lvl, index, cl)).all()
+                for add_first in (True, False):
+                    ext = oc.fast_rotation_ext(lvl, k, add_first, cl, digits, ra, rb)
+                    assert (ext == rc.fast_rotate_ext(lvl, index, add_first, cl)).all()
+                    assert (oc.keyswitch_ext(lvl, add_first, cl) == rc.keyswitch_ext(lvl, add_first, cl)).all()
+                assert (oc.keyswitch_down(lvl, ext) == rc.keyswitch_down(lvl, ext)).all()
     finally:
         oc.close()
         rc.close()
