@@ -250,6 +250,26 @@ int ofhe_ipc_export(ofhe_ctx* ctx, void* dptr, void* handle64_out);
 int ofhe_ipc_import(ofhe_ctx* ctx, const void* handle64, void** dptr_out);
 int ofhe_ipc_release(ofhe_ctx* ctx, void* dptr);
 
+/* ---- BFV homomorphic multiplication, HPSPOVERQ (BASELINE config 3): LeveledSHEBFVRNS::EvalMult
+ *      pke/lib/scheme/bfvrns/bfvrns-leveledshe.cpp:198-439 (tensor + t/P scale-and-round) and :735-741, 888-935
+ *      (RelinearizeCore).  `ring` registers Q (sizeQ limbs) then R (sizeR limbs).  The four conversions are built by
+ *      the caller with ofhe_bconv_create / ofhe_scale_round_create from CryptoParametersBFVRNS getters at level
+ *      l = sizeQ-1 (the tables embed long-double / BigInteger quotients, so they are inputs):
+ *        q_to_r_exact   mode 1, Q -> R: GetQlHatInvModq, GetQlHatModr, GetalphaQlModr, GetqInv
+ *        q_to_r_approx  mode 0, Q -> R: GetmNegRlQlHatInvModq, GetqInvModr
+ *        r_to_q_exact   mode 1, R -> Q: GetRlHatInvModr, GetRlHatModq, GetalphaRlModq, GetrInv
+ *        scale_round    mode 2, QR -> Q: GettQlSlHatInvModsDivsModq, GettQlSlHatInvModsDivsFrac
+ *      ct*_d [2][sizeQ][N] EVALUATION.  norelin: out3_d [3][sizeQ][N] COEFFICIENT (the reference's cvMult).  With
+ *      relinearisation: `hks` = HYBRID context over Q + P of the same crypto context, out_d [2][sizeQ][N] EVALUATION.   */
+typedef struct ofhe_bfv ofhe_bfv;
+int ofhe_bfv_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeR, const ofhe_bconv* q_to_r_exact,
+                    const ofhe_bconv* q_to_r_approx, const ofhe_bconv* r_to_q_exact, const ofhe_bconv* scale_round,
+                    ofhe_bfv** out);
+void ofhe_bfv_destroy(ofhe_bfv* b);
+int ofhe_bfv_evalmult_norelin(ofhe_bfv* b, const uint64_t* ct1_d, const uint64_t* ct2_d, uint64_t* out3_d, void* stream);
+int ofhe_bfv_evalmult(ofhe_bfv* b, ofhe_hks* hks, const uint64_t* ct1_d, const uint64_t* ct2_d, const ofhe_evk* evk,
+                      uint64_t* out_d, void* stream);
+
 /* fills dst_d [n_limbs][N] with uniform residues in [0, q_l) from a counter-based generator (synthetic inputs) */
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
                       void* stream);

@@ -5,6 +5,7 @@
 #include "../../include/ofhe_b200.h"
 #include "hks.h"
 #include "hostmath.h"
+#include "bfv.h"
 #include "shard.h"
 
 using namespace ofhe;
@@ -900,6 +901,46 @@ int ofhe_ipc_release(ofhe_ctx* ctx, void* dptr) {
     return guard([&] {
         OFHE_CUDA(cudaSetDevice(ctx->c->device));
         OFHE_CUDA(cudaIpcCloseMemHandle(dptr));
+    });
+}
+
+struct ofhe_bfv {
+    BfvMult* b;
+};
+int ofhe_bfv_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeR, const ofhe_bconv* q_to_r_exact,
+                    const ofhe_bconv* q_to_r_approx, const ofhe_bconv* r_to_q_exact, const ofhe_bconv* scale_round,
+                    ofhe_bfv** out) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE(q_to_r_exact && q_to_r_approx && r_to_q_exact && scale_round, "null conversion table");
+        for (const ofhe_bconv* t : {q_to_r_exact, q_to_r_approx, r_to_q_exact, scale_round})
+            OFHE_REQUIRE(t->r == ring->r, "conversion table belongs to another ring");
+        OFHE_REQUIRE(q_to_r_exact->t->mode == 1 && q_to_r_approx->t->mode == 0 && r_to_q_exact->t->mode == 1 &&
+                         scale_round->t->mode == 2,
+                     "conversion tables have the wrong kind (exact, approximate, exact, scale-and-round expected)");
+        auto* h = new ofhe_bfv();
+        h->b    = new BfvMult(ring->r, sizeQ, sizeR, q_to_r_exact->t.get(), q_to_r_approx->t.get(), r_to_q_exact->t.get(),
+                              scale_round->t.get());
+        *out    = h;
+    });
+}
+void ofhe_bfv_destroy(ofhe_bfv* b) {
+    if (b) {
+        delete b->b;
+        delete b;
+    }
+}
+int ofhe_bfv_evalmult_norelin(ofhe_bfv* b, const uint64_t* ct1_d, const uint64_t* ct2_d, uint64_t* out3_d, void* stream) {
+    return guard([&] {
+        use(b->b->ring);
+        b->b->evalmult_norelin(ct1_d, ct2_d, out3_d, S(stream));
+    });
+}
+int ofhe_bfv_evalmult(ofhe_bfv* b, ofhe_hks* hks, const uint64_t* ct1_d, const uint64_t* ct2_d, const ofhe_evk* evk,
+                      uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(b->b->ring);
+        b->b->evalmult(*hks->h, ct1_d, ct2_d, *evk->k, out_d, S(stream));
     });
 }
 

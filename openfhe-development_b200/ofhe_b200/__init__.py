@@ -81,6 +81,10 @@ SIGNATURES = {
     "ofhe_shard_evalmult_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_b": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_c": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_bfv_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "ofhe_bfv_destroy": (None, [_vp]),
+    "ofhe_bfv_evalmult_norelin": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "ofhe_bfv_evalmult": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_a_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_b_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_peer_flags_words": (C.c_size_t, [C.c_uint32, C.c_uint32]),
@@ -349,6 +353,39 @@ class BaseConv:
         if self.h:
             lib().ofhe_bconv_destroy(self.h)
             self.h = None
+
+
+class BfvMult:
+    """BFV EvalMult, HPSPOVERQ (LeveledSHEBFVRNS::EvalMult): `ring` registers Q then R; `T` holds the reference's
+    CryptoParametersBFVRNS tables at level sizeQ-1 under the getter names without the `Get` prefix."""
+
+    def __init__(self, ring, sizeQ, sizeR, T):
+        self.ring, self.sizeQ, self.sizeR = ring, sizeQ, sizeR
+        iq, ir = list(range(sizeQ)), list(range(sizeQ, sizeQ + sizeR))
+        B = BaseConv
+        self.convs = [
+            B.switch_crt_basis(ring, iq, T["QlHatInvModq"], ir, T["QlHatModr"], True, T["alphaQlModr"], T["qInv"]),
+            B.switch_crt_basis(ring, iq, T["mNegRlQlHatInvModq"], ir, T["qInvModr"], False),
+            B.switch_crt_basis(ring, ir, T["RlHatInvModr"], iq, T["RlHatModq"], True, T["alphaRlModq"], T["rInv"]),
+            B.scale_and_round(ring, ir, iq, True, T["tQlSlHatInvModsDivsModq"], T["tQlSlHatInvModsDivsFrac"]),
+        ]
+        h = _vp()
+        _ck(lib().ofhe_bfv_create(ring.h, sizeQ, sizeR, *[c.h for c in self.convs], C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().ofhe_bfv_destroy(self.h)
+            self.h = None
+        for c in self.convs:
+            c.close()
+        self.convs = []
+
+    def evalmult_norelin(self, ct1, ct2, out3):
+        _ck(lib().ofhe_bfv_evalmult_norelin(self.h, _ptr(ct1), _ptr(ct2), _ptr(out3), _stream()))
+
+    def evalmult(self, hks, ct1, ct2, evk, out):
+        _ck(lib().ofhe_bfv_evalmult(self.h, hks.h, _ptr(ct1), _ptr(ct2), evk.h, _ptr(out), _stream()))
 
 
 class EvalKey:

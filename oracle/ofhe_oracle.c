@@ -558,6 +558,27 @@ orc_ckks* orc_ckks_create(uint32_t N, uint32_t depth, uint32_t scaleBits, uint32
     }
     return c;
 }
+/* the same hybrid key-switch context over a caller-supplied chain (BFV's Q and P, rns-cryptoparameters.cpp:48-401
+ * is scheme independent): moduli / roots = Q (sizeQ) then P (sizeP); numPerPartQ = ceil(sizeQ / dnum) (:86-97) */
+orc_ckks* orc_hks_create_from_moduli(uint32_t N, uint32_t sizeQ, uint32_t sizeP, uint32_t dnum, const uint64_t* moduli,
+                                     const uint64_t* roots) {
+    orc_ckks* c = (orc_ckks*)calloc(1, sizeof(orc_ckks));
+    uint32_t tot = sizeQ + sizeP;
+    c->N = N, c->sizeQ = sizeQ, c->sizeP = sizeP, c->dnum = dnum, c->alpha = (sizeQ + dnum - 1) / dnum;
+    c->q     = (uint64_t*)malloc(sizeof(uint64_t) * tot);
+    c->rq    = (uint64_t*)malloc(sizeof(uint64_t) * tot);
+    c->nInv  = (uint64_t*)malloc(sizeof(uint64_t) * tot);
+    c->nInvP = (uint64_t*)malloc(sizeof(uint64_t) * tot);
+    c->tw    = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)tot * 4 * N);
+    memcpy(c->q, moduli, sizeof(uint64_t) * tot);
+    memcpy(c->rq, roots, sizeof(uint64_t) * tot);
+#pragma omp parallel for schedule(dynamic)
+    for (uint32_t i = 0; i < tot; ++i) {
+        uint64_t* t = c->tw + (size_t)i * 4 * N;
+        orc_twiddles(c->q[i], c->rq[i], N, t, t + N, t + 2 * N, t + 3 * N, &c->nInv[i], &c->nInvP[i]);
+    }
+    return c;
+}
 void orc_ckks_destroy(orc_ckks* c) {
     if (!c)
         return;

@@ -63,6 +63,9 @@ typedef struct orc_ckks orc_ckks;
 /* scal_tech: 0 FIXEDMANUAL, 1 FIXEDAUTO, 2 FLEXIBLEAUTO (FLEXIBLEAUTOEXT not restated) */
 orc_ckks* orc_ckks_create(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
                           int scal_tech);
+/* hybrid key-switch context over a caller-supplied chain (e.g. BFV's Q then P) */
+orc_ckks* orc_hks_create_from_moduli(uint32_t N, uint32_t sizeQ, uint32_t sizeP, uint32_t dnum, const uint64_t* moduli,
+                                     const uint64_t* roots);
 void orc_ckks_destroy(orc_ckks* c);
 void orc_ckks_shape(const orc_ckks* c, uint32_t* shape /* N,sizeQ,sizeP,dnum,alpha */);
 void orc_ckks_moduli(const orc_ckks* c, uint64_t* moduli, uint64_t* roots);

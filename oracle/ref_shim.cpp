@@ -853,4 +853,55 @@ int ref_bfv_evalmult_norelin(void* hv, const uint64_t* ct1, const uint64_t* ct2,
     });
 }
 
+// key-switching side of the BFV context (HYBRID): shape = sizeP, dnum (numPartQ), alpha (numPerPartQ); P moduli / roots
+void ref_bfv_ks_shape(void* hv, uint32_t* shape, uint64_t* moduliP, uint64_t* rootsP) {
+    auto* h  = static_cast<BfvCtx*>(hv);
+    const auto& pp = h->cp->GetParamsP()->GetParams();
+    shape[0] = pp.size();
+    shape[1] = h->cp->GetNumPartQ();
+    shape[2] = h->cp->GetNumPerPartQ();
+    if (moduliP)
+        for (size_t i = 0; i < pp.size(); ++i) {
+            moduliP[i] = pp[i]->GetModulus().ConvertToInt<uint64_t>();
+            rootsP[i]  = pp[i]->GetRootOfUnity().ConvertToInt<uint64_t>();
+        }
+}
+// relinearisation key: a, b as [dnum][sizeQ+sizeP][N] EVALUATION
+int ref_bfv_evalmult_key(void* hv, uint64_t* a, uint64_t* b) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        const auto& ek = h->cc->GetEvalMultKeyVector(h->keys.secretKey->GetKeyTag())[0];
+        const auto& av = ek->GetAVector();
+        const auto& bv = ek->GetBVector();
+        size_t stride  = (size_t)(h->sizeQ + h->cp->GetParamsP()->GetParams().size()) * h->N;
+        for (size_t j = 0; j < av.size(); ++j) {
+            dump_poly(av[j], a + j * stride);
+            dump_poly(bv[j], b + j * stride);
+        }
+    });
+}
+// cc->EvalMult(ct1, ct2) (HPSPOVERQ tensor + RelinearizeCore, bfvrns-leveledshe.cpp:735-741,888-935):
+// ct* = 2 polys [sizeQ][N] EVALUATION -> out = 2 polys [sizeQ][N] EVALUATION
+int ref_bfv_evalmult(void* hv, const uint64_t* ct1, const uint64_t* ct2, uint64_t* out) {
+    auto* h = static_cast<BfvCtx*>(hv);
+    return guarded([&] {
+        auto mk = [&](const uint64_t* d) {
+            auto ct = h->tmpl->Clone();
+            std::vector<DCRTPoly> el;
+            for (uint32_t k = 0; k < 2; ++k)
+                el.push_back(make_poly(bfv_params(h, 0), Format::EVALUATION, d + (size_t)k * h->sizeQ * h->N));
+            ct->SetElements(std::move(el));
+            return ct;
+        };
+        auto c = h->cc->EvalMult(mk(ct1), mk(ct2));
+        if (c->GetElements().size() != 2)
+            OPENFHE_THROW("unexpected BFV EvalMult output shape");
+        for (uint32_t k = 0; k < 2; ++k) {
+            DCRTPoly e = c->GetElements()[k];
+            e.SetFormat(Format::EVALUATION);
+            dump_poly(e, out + (size_t)k * h->sizeQ * h->N);
+        }
+    });
+}
+
 }  // extern "C"

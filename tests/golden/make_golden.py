@@ -97,6 +97,9 @@ def main():
         b = r.bfv(*args)
         g = dict(args=np.array(args, dtype=np.int64), shape=np.array([b.N, b.sizeQ, b.sizeR]), moduli=b.moduli,
                  roots=b.roots)
+        if not with_data:
+            ks = b.ks_shape()
+            g.update(ks_shape=np.array([ks["sizeP"], ks["dnum"], ks["alpha"]]), moduliP=ks["moduliP"], rootsP=ks["rootsP"])
         for k, v in b.tables().items():
             g["T_" + k] = v
         if with_data:
@@ -113,6 +116,11 @@ def main():
             ct1 = np.stack([seeded_residues(603, Q, b.N), seeded_residues(604, Q, b.N)])
             ct2 = np.stack([seeded_residues(605, Q, b.N), seeded_residues(606, Q, b.N)])
             g.update(ct1=ct1, ct2=ct2, evalmult_norelin=b.evalmult_norelin(ct1, ct2))
+            # relinearised product (HYBRID key switch of the BFV context): P moduli, key, cc->EvalMult output
+            ks = b.ks_shape()
+            ea, eb = b.evalmult_key()
+            g.update(ks_shape=np.array([ks["sizeP"], ks["dnum"], ks["alpha"]]), moduliP=ks["moduliP"], rootsP=ks["rootsP"],
+                     evk_a=ea, evk_b=eb, evalmult=b.evalmult(ct1, ct2))
         print(tag, "sizeQ", b.sizeQ, "sizeR", b.sizeR)
         np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **g)
         b.close()

@@ -92,6 +92,7 @@ class Oracle:
              u64p, u64p)
         _sig(L, "orc_scale_and_round", None, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_int, u64p, f64p, u64p, u64p)
         _sig(L, "orc_ckks_create", C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int)
+        _sig(L, "orc_hks_create_from_moduli", C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u64p)
         _sig(L, "orc_ckks_destroy", None, C.c_void_p)
         _sig(L, "orc_ckks_shape", None, C.c_void_p, u32p)
         _sig(L, "orc_ckks_moduli", None, C.c_void_p, u64p, u64p)
@@ -198,6 +199,10 @@ class Oracle:
     def ckks(self, N, depth, scale_bits, first_bits, dnum=0, scal_tech=0):
         return OracleCkks(self, N, depth, scale_bits, first_bits, dnum, scal_tech)
 
+    def hks_from_moduli(self, N, sizeQ, sizeP, dnum, moduli, roots):
+        """Hybrid key-switch context (a16-a18, a20) over a caller-supplied chain, e.g. BFV's Q then P."""
+        return OracleCkks(self, N, 0, 0, 0, dnum, 0, from_moduli=(sizeQ, sizeP, moduli, roots))
+
 
 class _CkksCommon:
     """Shape + table accessors shared by OracleCkks and ReferenceCkks (same method names on purpose)."""
@@ -220,10 +225,15 @@ class _CkksCommon:
 
 
 class OracleCkks(_CkksCommon):
-    def __init__(self, orc, N, depth, scale_bits, first_bits, dnum, scal_tech):
+    def __init__(self, orc, N, depth, scale_bits, first_bits, dnum, scal_tech, from_moduli=None):
         self.o = orc
         self.L = orc.L
-        self.h = self.L.orc_ckks_create(N, depth, scale_bits, first_bits, dnum, scal_tech)
+        if from_moduli is not None:  # hybrid key-switch context over a given chain: (sizeQ, sizeP, moduli, roots)
+            sq, sp, mod, rts = from_moduli
+            self.h = self.L.orc_hks_create_from_moduli(N, sq, sp, dnum, np.ascontiguousarray(mod, dtype=np.uint64),
+                                                       np.ascontiguousarray(rts, dtype=np.uint64))
+        else:
+            self.h = self.L.orc_ckks_create(N, depth, scale_bits, first_bits, dnum, scal_tech)
         s = np.zeros(6, dtype=np.uint32)
         self.L.orc_ckks_shape(self.h, s)
         self._init_shape(s)
@@ -399,6 +409,9 @@ class Reference:
                   "ref_bfv_scale_and_round"):
             _sig(L, n, C.c_int, C.c_void_p, u64p, u64p)
         _sig(L, "ref_bfv_evalmult_norelin", C.c_int, C.c_void_p, u64p, u64p, u64p)
+        _sig(L, "ref_bfv_ks_shape", None, C.c_void_p, u32p, C.c_void_p, C.c_void_p)
+        _sig(L, "ref_bfv_evalmult_key", C.c_int, C.c_void_p, u64p, u64p)
+        _sig(L, "ref_bfv_evalmult", C.c_int, C.c_void_p, u64p, u64p, u64p)
         _sig(L, "ref_ckks_encrypt", C.c_int, C.c_void_p, f64p, C.c_uint32, u64p)
         _sig(L, "ref_ckks_decrypt", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, u64p, f64p, C.c_uint32)
 
@@ -678,4 +691,24 @@ class ReferenceBfv:
     def evalmult_norelin(self, ct1, ct2):
         out = np.empty((3, self.sizeQ, self.N), dtype=np.uint64)
         self.r._ok(self.L.ref_bfv_evalmult_norelin(self.h, np.ascontiguousarray(ct1), np.ascontiguousarray(ct2), out))
+        return out
+
+    def ks_shape(self):
+        """HYBRID key-switching side: dict(sizeP, dnum, alpha, moduliP, rootsP)."""
+        s = np.zeros(3, dtype=np.uint32)
+        self.L.ref_bfv_ks_shape(self.h, s, None, None)
+        mp, rp = np.empty(int(s[0]), dtype=np.uint64), np.empty(int(s[0]), dtype=np.uint64)
+        self.L.ref_bfv_ks_shape(self.h, s, mp.ctypes.data, rp.ctypes.data)
+        return dict(sizeP=int(s[0]), dnum=int(s[1]), alpha=int(s[2]), moduliP=mp, rootsP=rp)
+
+    def evalmult_key(self):
+        ks = self.ks_shape()
+        a = np.empty((ks["dnum"], self.sizeQ + ks["sizeP"], self.N), dtype=np.uint64)
+        b = np.empty_like(a)
+        self.r._ok(self.L.ref_bfv_evalmult_key(self.h, a, b))
+        return a, b
+
+    def evalmult(self, ct1, ct2):
+        out = np.empty((2, self.sizeQ, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_bfv_evalmult(self.h, np.ascontiguousarray(ct1), np.ascontiguousarray(ct2), out))
         return out

@@ -57,6 +57,28 @@ def test_oracle_vs_golden(oracle, golden, name):
         assert (out == g["evalmult_norelin"][k]).all(), k
 
 
+def oracle_evalmult_relin(oracle, g):
+    """RelinearizeCore on the reference's own 3-element product (bfvrns-leveledshe.cpp:888-935): NTT, hybrid
+    KeySwitchCore of c2 over BFV's Q and P, c0 += ab0, c1 += ab1.  Returns [2][sizeQ][N] EVALUATION."""
+    N, sizeQ, _ = (int(v) for v in g["shape"])
+    sizeP, dnum, alpha = (int(v) for v in g["ks_shape"])
+    Q, rQ = g["moduli"][:sizeQ], g["roots"][:sizeQ]
+    h = oracle.hks_from_moduli(N, sizeQ, sizeP, dnum, np.concatenate([Q, g["moduliP"]]), np.concatenate([rQ, g["rootsP"]]))
+    try:
+        assert h.alpha == alpha
+        c = [oracle.dcrt_switch_format(Q, rQ, g["evalmult_norelin"][k], False) for k in range(3)]
+        ab0, ab1 = h.keyswitch_core(sizeQ, c[2], g["evk_a"], g["evk_b"])
+        return np.stack([oracle.dcrt_binop(Q, 0, c[0], ab0), oracle.dcrt_binop(Q, 0, c[1], ab1)])
+    finally:
+        h.close()
+
+
+@pytest.mark.parametrize("name", ["bfv_n64", "bfv_n128_d4"])
+def test_oracle_relinearised_product_golden(oracle, golden, name):
+    g = golden(name)
+    assert (oracle_evalmult_relin(oracle, g) == g["evalmult"]).all()
+
+
 class _Tables(dict):
     """dict with the `.files` attribute of an npz archive, for contexts created live from the reference"""
 
@@ -156,6 +178,43 @@ class DeviceBfv:
         return np.stack(outs)
 
 
+class ProductBfv:
+    """The library's own BFV multiplication (csrc/bfv.cu) plus the HYBRID context over Q + P for relinearisation."""
+
+    def __init__(self, gpu, g, ks=None):
+        self.ctx, m = gpu
+        self.N, self.sizeQ, self.sizeR = (int(v) for v in g["shape"])
+        self.ring = m.Ring(self.ctx, self.N, g["moduli"], g["roots"])
+        self.mult = m.BfvMult(self.ring, self.sizeQ, self.sizeR, _T(g))
+        self.hks = self.ring_ks = None
+        ks = ks or ({"sizeP": int(g["ks_shape"][0]), "dnum": int(g["ks_shape"][1]), "moduliP": g["moduliP"],
+                     "rootsP": g["rootsP"]} if "ks_shape" in g.files else None)
+        if ks:
+            nQ = self.sizeQ
+            self.ring_ks = m.Ring(self.ctx, self.N, np.concatenate([g["moduli"][:nQ], ks["moduliP"]]),
+                                  np.concatenate([g["roots"][:nQ], ks["rootsP"]]))
+            self.hks = m.Hks(self.ring_ks, nQ, ks["sizeP"], ks["dnum"])
+        self.m = m
+
+    def close(self):
+        for o in (self.hks, self.ring_ks, self.mult, self.ring):
+            if o is not None:
+                o.close()
+
+    def evalmult_norelin(self, ct1, ct2):
+        out = self.ctx.zeros(3, self.sizeQ, self.N)
+        self.mult.evalmult_norelin(self.ctx.upload(ct1), self.ctx.upload(ct2), out)
+        return self.ctx.download(out).copy()
+
+    def evalmult(self, ct1, ct2, evk_a, evk_b):
+        evk = self.m.EvalKey(self.hks, evk_a, evk_b)
+        out = self.ctx.zeros(2, self.sizeQ, self.N)
+        self.mult.evalmult(self.hks, self.ctx.upload(ct1), self.ctx.upload(ct2), evk, out)
+        res = self.ctx.download(out).copy()
+        evk.close()
+        return res
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["bfv_n64", "bfv_n128_d4"])
 def test_gpu_vs_golden(gpu, golden, name):
@@ -175,6 +234,13 @@ def test_gpu_vs_golden(gpu, golden, name):
         assert (d.evalmult_norelin(g["ct1"], g["ct2"]) == g["evalmult_norelin"]).all()
     finally:
         d.close()
+    # the product entry points (ofhe_bfv_evalmult_norelin / ofhe_bfv_evalmult): same vectors
+    p = ProductBfv(gpu, g)
+    try:
+        assert (p.evalmult_norelin(g["ct1"], g["ct2"]) == g["evalmult_norelin"]).all()
+        assert (p.evalmult(g["ct1"], g["ct2"], g["evk_a"], g["evk_b"]) == g["evalmult"]).all()
+    finally:
+        p.close()
 
 
 @pytest.mark.gpu
@@ -207,6 +273,23 @@ def test_gpu_config3_size_vs_oracle(gpu, oracle, golden):
         d.sr.apply(ctx.upload(xq), o)
         assert (ctx.download(o) == oracle.scale_and_round(Q, True, T["tQlSlHatInvModsDivsModq"],
                                                           T["tQlSlHatInvModsDivsFrac"], xq)).all()
+        # the product entry points at this size: the fused device composition equals the step-by-step one (whose
+        # pieces are pinned above), and the relinearised product equals NTT + the oracle's hybrid key switch
+        ct1 = np.stack([seeded_residues(710, Q, N), seeded_residues(711, Q, N)])
+        ct2 = np.stack([seeded_residues(712, Q, N), seeded_residues(713, Q, N)])
+        want3 = d.evalmult_norelin(ct1, ct2)
+        p = ProductBfv(gpu, g)
+        try:
+            assert (p.evalmult_norelin(ct1, ct2) == want3).all()
+            sizeP, dnum, _ = (int(v) for v in g["ks_shape"])
+            qp = np.concatenate([Q, g["moduliP"]])
+            ea = seeded_residues(714, np.tile(qp, dnum), N).reshape(dnum, nQ + sizeP, N)
+            eb = seeded_residues(715, np.tile(qp, dnum), N).reshape(dnum, nQ + sizeP, N)
+            g2 = dict(shape=g["shape"], ks_shape=g["ks_shape"], moduli=g["moduli"], roots=g["roots"],
+                      moduliP=g["moduliP"], rootsP=g["rootsP"], evalmult_norelin=want3, evk_a=ea, evk_b=eb)
+            assert (p.evalmult(ct1, ct2, ea, eb) == oracle_evalmult_relin(oracle, g2)).all()
+        finally:
+            p.close()
     finally:
         d.close()
 
@@ -219,7 +302,15 @@ def test_gpu_vs_reference_live(gpu, reference):
         Q = b.moduli[:b.sizeQ]
         ct1 = np.stack([seeded_residues(1, Q, b.N), seeded_residues(2, Q, b.N)])
         ct2 = np.stack([seeded_residues(3, Q, b.N), seeded_residues(4, Q, b.N)])
-        assert (d.evalmult_norelin(ct1, ct2) == b.evalmult_norelin(ct1, ct2)).all()
+        want3 = b.evalmult_norelin(ct1, ct2)
+        assert (d.evalmult_norelin(ct1, ct2) == want3).all()
         d.close()
+        p = ProductBfv(gpu, _live_tables(b), ks=b.ks_shape())
+        try:
+            assert (p.evalmult_norelin(ct1, ct2) == want3).all()
+            ea, eb = b.evalmult_key()
+            assert (p.evalmult(ct1, ct2, ea, eb) == b.evalmult(ct1, ct2)).all()
+        finally:
+            p.close()
     finally:
         b.close()
