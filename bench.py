@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=2, help="N>1: pipeline slots (independent multiplications in flight)")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N>1: limb exchange by NVLink peer stores fused into the INTT (default) or NCCL all-gathers")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="N>1 push mode: eager launches, no CUDA graphs")
@@ -222,7 +223,7 @@ def main():
         # ---- limb-sharded across the ranks (SURVEY 8 e): one EvalMult is split by RNS limb; two NCCL all-gathers per
         #      step (ModUp sources, ModDown P limbs).  Two pipeline slots on two streams let the all-gathers of one
         #      multiplication overlap the kernels of the next (steps are independent ciphertext pairs).
-        n_slots = 2
+        n_slots = max(1, a.slots)
         shards = [m.Shard(ring, sizeQ, sizeP, dnum, rank, world) for _ in range(n_slots)]
         info = shards[0].info(sizeQl)
         own_q, own_p = shards[0].owned(sizeQl)
