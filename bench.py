@@ -124,7 +124,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slots", type=int, default=2, help="N>1: pipeline slots (independent multiplications in flight)")
+    ap.add_argument("--slots", type=int, default=4, help="N>1: pipeline slots (independent multiplications in flight)")
+    ap.add_argument("--slots1", type=int, default=2, help="N=1: independent multiplications in flight (streams)")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N>1: limb exchange by NVLink peer stores fused into the INTT (default) or NCCL all-gathers")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="N>1 push mode: eager launches, no CUDA graphs")
@@ -184,19 +185,44 @@ def main():
         ring.fill_uniform(ct1.view(2 * sizeQl, N), idx2, 11)
         ring.fill_uniform(ct2.view(2 * sizeQl, N), idx2, 12)
         # ---- device-resident throughput ------------------------------------------------------------------------
-        for _ in range(a.warmup):
-            hks.evalmult(sizeQl, ct1, ct2, evk, out)
+        # independent multiplications are issued round-robin on `slots` streams, each slot with its own context
+        # (scratch arena), tables and key copy: the tail of one multiplication's small launches overlaps the next one
+        n_slots = max(1, a.slots1)
+        extra = []
+        slot_objs = [(hks, evk, out)]
+        for s_ in range(1, n_slots):
+            c_s = m.Context(local_rank)
+            r_s = m.Ring(c_s, N, p["moduli"], p["roots"])
+            h_s = m.Hks(r_s, sizeQ, sizeP, dnum)
+            k_s = m.EvalKey(h_s, seed=1234)
+            slot_objs.append((h_s, k_s, ctx.zeros(2, sizeQl, N)))
+            extra += [k_s, h_s, r_s, c_s]
+        streams = [torch.cuda.Stream() for _ in range(n_slots)]
+
+        def run(nsteps):
+            cur = torch.cuda.current_stream()
+            for st in streams:
+                st.wait_stream(cur)
+            for k in range(nsteps):
+                h_s, k_s, o_s = slot_objs[k % n_slots]
+                with torch.cuda.stream(streams[k % n_slots]):
+                    h_s.evalmult(sizeQl, ct1, ct2, k_s, o_s)
+            for st in streams:
+                cur.wait_stream(st)
+
+        run(max(a.warmup, n_slots))
         barrier()
         sampler.start()
         e0.record()
-        for _ in range(a.steps):
-            hks.evalmult(sizeQl, ct1, ct2, evk, out)
+        run(a.steps)
         e1.record()
         barrier()
         sampler.stop_flag.set()
         ms = max_over_ranks(e0.elapsed_time(e1))
         value = a.steps / (ms * 1e-3)
-        parallelism, scaling, launches = "single GPU", "weak", LAUNCHES_PER_STEP
+        for s_ in range(1, n_slots):
+            assert bool((slot_objs[s_][2] == out).all()), "pipeline slots disagree"
+        parallelism, scaling, launches = f"single GPU, {n_slots} independent multiplications in flight", "weak", LAUNCHES_PER_STEP
         # ---- end to end through the host-buffer entry point (pinned host memory, copies inside the timed region)
         h1 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
         h2 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
@@ -218,7 +244,7 @@ def main():
         assert bool((ho.cuda() == out).all()), "host-buffer path and device path disagree"
         for hb in (hos[0], hos[-1]):
             assert bool((hb == ho).all()), "pipelined host path disagrees with the single-call host path"
-        closers = [evk, hks]
+        closers = extra + [evk, hks]
     else:
         # ---- limb-sharded across the ranks (SURVEY 8 e): one EvalMult is split by RNS limb; two NCCL all-gathers per
         #      step (ModUp sources, ModDown P limbs).  Two pipeline slots on two streams let the all-gathers of one
