@@ -257,8 +257,67 @@ public:
         check(ofhe_hks_keyswitch_core(m_hks, sizeQl, a.device_data(), evalKey, both.device_data(), nullptr));
         return {slice(both, 0, sizeQl, N), slice(both, 1, sizeQl, N)};
     }
+    // EvalFastKeySwitchCoreExt(digits, evalKey, paramsQl) -> (cTilda[0], cTilda[1]) over QlP (:402-435)
+    std::pair<DCRTPoly, DCRTPoly> EvalFastKeySwitchCoreExt(const std::vector<DCRTPoly>& digits, const ofhe_evk* evalKey,
+                                                           uint32_t sizeQl) const {
+        const size_t N = digits.at(0).GetRingDimension(), sizeQlP = sizeQl + m_sizeP;
+        DCRTPoly slab = pack(digits, sizeQl);
+        DCRTPoly both(m_params, repeat(towersQlP(sizeQl), 2), EVALUATION);
+        check(ofhe_hks_inner_product(m_hks, sizeQl, slab.device_data(), evalKey, both.device_data(), nullptr));
+        return {sliceExt(both, 0, sizeQl, N, sizeQlP), sliceExt(both, 1, sizeQl, N, sizeQlP)};
+    }
+    // EvalFastKeySwitchCore(digits, evalKey, paramsQl) = the above + ApproxModDown of both (:381-400)
+    std::pair<DCRTPoly, DCRTPoly> EvalFastKeySwitchCore(const std::vector<DCRTPoly>& digits, const ofhe_evk* evalKey,
+                                                        uint32_t sizeQl) const {
+        const size_t N = digits.at(0).GetRingDimension(), sizeQlP = sizeQl + m_sizeP;
+        DCRTPoly slab = pack(digits, sizeQl);
+        DCRTPoly ext(m_params, repeat(towersQlP(sizeQl), 2), EVALUATION);
+        check(ofhe_hks_inner_product(m_hks, sizeQl, slab.device_data(), evalKey, ext.device_data(), nullptr));
+        DCRTPoly both(m_params, repeat(towersQl(sizeQl), 2), EVALUATION);
+        check(ofhe_hks_approx_mod_down(m_hks, sizeQl, ext.device_data(), both.device_data(), 2, nullptr));
+        (void)sizeQlP;
+        return {slice(both, 0, sizeQl, N), slice(both, 1, sizeQl, N)};
+    }
+    // KeySwitchExt(ciphertext, addFirst) (:217-243): (c0, c1) over Ql -> over QlP as [c_k * (P mod q_i) | 0]
+    std::pair<DCRTPoly, DCRTPoly> KeySwitchExt(const DCRTPoly& c0, const DCRTPoly& c1, bool addFirst) const {
+        const uint32_t sizeQl = (uint32_t)c0.GetNumOfElements();
+        const size_t N = c0.GetRingDimension(), sizeQlP = sizeQl + m_sizeP;
+        DCRTPoly in(m_params, repeat(towersQl(sizeQl), 2), EVALUATION);
+        check(ofhe_memcpy_d2d(m_params->ctx(), in.device_data(), c0.device_data(), sizeQl * N * sizeof(uint64_t), nullptr));
+        check(ofhe_memcpy_d2d(m_params->ctx(), in.device_data() + (size_t)sizeQl * N, c1.device_data(),
+                              sizeQl * N * sizeof(uint64_t), nullptr));
+        DCRTPoly both(m_params, repeat(towersQlP(sizeQl), 2), EVALUATION);
+        check(ofhe_hks_keyswitch_ext(m_hks, sizeQl, addFirst ? 1 : 0, in.device_data(), both.device_data(), nullptr));
+        return {sliceExt(both, 0, sizeQl, N, sizeQlP), sliceExt(both, 1, sizeQl, N, sizeQlP)};
+    }
+    // KeySwitchDown(ciphertext) (:246-277): ApproxModDown of both polynomials of an extended ciphertext
+    std::pair<DCRTPoly, DCRTPoly> KeySwitchDown(const DCRTPoly& e0, const DCRTPoly& e1) const {
+        const uint32_t sizeQl = (uint32_t)e0.GetNumOfElements() - m_sizeP;
+        const size_t N = e0.GetRingDimension(), sizeQlP = sizeQl + m_sizeP;
+        DCRTPoly in(m_params, repeat(towersQlP(sizeQl), 2), EVALUATION);
+        check(ofhe_memcpy_d2d(m_params->ctx(), in.device_data(), e0.device_data(), sizeQlP * N * sizeof(uint64_t), nullptr));
+        check(ofhe_memcpy_d2d(m_params->ctx(), in.device_data() + sizeQlP * N, e1.device_data(),
+                              sizeQlP * N * sizeof(uint64_t), nullptr));
+        DCRTPoly both(m_params, repeat(towersQl(sizeQl), 2), EVALUATION);
+        check(ofhe_hks_approx_mod_down(m_hks, sizeQl, in.device_data(), both.device_data(), 2, nullptr));
+        return {slice(both, 0, sizeQl, N), slice(both, 1, sizeQl, N)};
+    }
 
 private:
+    DCRTPoly pack(const std::vector<DCRTPoly>& digits, uint32_t sizeQl) const {  // digits -> one [nd][QlP][N] slab
+        const size_t N = digits.at(0).GetRingDimension(), sizeQlP = sizeQl + m_sizeP;
+        DCRTPoly slab(m_params, repeat(towersQlP(sizeQl), (uint32_t)digits.size()), EVALUATION);
+        for (size_t j = 0; j < digits.size(); ++j)
+            check(ofhe_memcpy_d2d(m_params->ctx(), slab.device_data() + j * sizeQlP * N, digits[j].device_data(),
+                                  sizeQlP * N * sizeof(uint64_t), nullptr));
+        return slab;
+    }
+    DCRTPoly sliceExt(const DCRTPoly& both, uint32_t k, uint32_t sizeQl, size_t N, size_t sizeQlP) const {
+        DCRTPoly r(m_params, towersQlP(sizeQl), EVALUATION);
+        check(ofhe_memcpy_d2d(m_params->ctx(), r.device_data(), both.device_data() + (size_t)k * sizeQlP * N,
+                              sizeQlP * N * sizeof(uint64_t), nullptr));
+        return r;
+    }
     std::vector<uint32_t> towersQl(uint32_t sizeQl) const {
         std::vector<uint32_t> t(sizeQl);
         for (uint32_t i = 0; i < sizeQl; ++i)

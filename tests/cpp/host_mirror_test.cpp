@@ -124,6 +124,28 @@ int main() {
         EXPECT(digits.size() == 2 && digits[0].GetNumOfElements() == sizeQ + sizeP);
         auto ba = ks.KeySwitchCore(zero, evk);
         EXPECT(ba.first == zero && ba.second == zero);
+        // KeySwitchCore(a) == EvalFastKeySwitchCore(EvalKeySwitchPrecomputeCore(a)) == KeySwitchDown(EvalFastKeySwitchCoreExt(..))
+        // on a non-zero polynomial (the reference composes them exactly this way, keyswitch-hybrid.cpp:308-312,381-400)
+        DCRTPoly a(p, t, EVALUATION, true);
+        {
+            std::vector<uint64_t> h(1u << 12);
+            for (uint32_t i = 0; i < sizeQ; ++i) {
+                for (uint32_t j = 0; j < (1u << 12); ++j)
+                    h[j] = (0x9E3779B97F4A7C15ull * (i * 4099ull + j + 1)) % q[i];
+                a.SetElementAtIndex(i, h);
+            }
+        }
+        auto dg   = ks.EvalKeySwitchPrecomputeCore(a);
+        auto core = ks.KeySwitchCore(a, evk);
+        auto fast = ks.EvalFastKeySwitchCore(dg, evk, sizeQ);
+        EXPECT(core.first == fast.first && core.second == fast.second);
+        auto ext  = ks.EvalFastKeySwitchCoreExt(dg, evk, sizeQ);
+        EXPECT(ext.first.GetNumOfElements() == sizeQ + sizeP);
+        auto down = ks.KeySwitchDown(ext.first, ext.second);
+        EXPECT(core.first == down.first && core.second == down.second);
+        auto lifted = ks.KeySwitchExt(a, a, false);
+        auto back   = ks.KeySwitchDown(lifted.first, lifted.second);   // ModDown([c * P | 0]) == c, and 0 for the skipped c0
+        EXPECT(back.second == a && back.first == zero);
         ofhe_evk_destroy(evk);
     }
     if (failures == 0)
