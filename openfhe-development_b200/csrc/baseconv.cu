@@ -16,7 +16,10 @@
 // multiply itself.  The 60x60-bit multiply-accumulate works on 30-bit halves so that each MAC is exactly four
 // IMAD.WIDE.U32 with NO carry chain:
 //     y = y1*2^30 + y0,  m = m1*2^30 + m0   ->   c0 += y0*m0; c1a += y0*m1; c1b += y1*m0; c2 += y1*m1
-// Each partial sum stays below 2^64 for 16 terms.  The four column sums are then assembled into one 128-bit integer
+// Each partial sum stays below 2^64 for 16 terms.  For up to 16 source limbs (every conversion of config 2) the MAC is
+// three products instead (Karatsuba on the halves: the middle column is c0 + c2 - sum (y1-y0)(m1-m0), a signed
+// IMAD.WIDE whose 16 terms are split over two int64 accumulators) -- the multiplier pipe is the kernel's bound.
+// The four column sums are then assembled into one 128-bit integer
 // S = c0 + (c1a + c1b) 2^30 + c2 2^60 (shifts and adds only) and reduced by a single 128 -> 64 Barrett step per output
 // (~14 multiplier instructions; reducing the four columns separately with Shoup-lazy products took ~32).  The matrix
 // slice of the CTA's output group is zero-padded in shared memory to 16*CH x JPT, so the MAC loops have compile-time
@@ -31,6 +34,9 @@ namespace {
 constexpr uint32_t kMask30 = (1u << 30) - 1;
 #ifndef OFHE_BCONV_JPT
 #define OFHE_BCONV_JPT 16
+#endif
+#ifndef OFHE_BCONV_KARA
+#define OFHE_BCONV_KARA 1  // 1: three products per 60x60 MAC (Karatsuba on the 30-bit halves) for <= 16 source limbs, mode 0
 #endif
 #ifndef OFHE_BCONV_MINB
 #define OFHE_BCONV_MINB 1
@@ -70,6 +76,12 @@ __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c)
 }
 
 
+__device__ __forceinline__ int64_t mad_wide_s(int32_t a, int32_t b, int64_t c) {
+    int64_t d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
 // CH chunks of 16 source limbs; kCPT coefficients per thread (2 when the register budget allows: every 128-bit
 // matrix read from shared memory then feeds 16 IMADs)
 template <int CH, int kCPT, int MODE>  // MODE is a template parameter so that the a10 instance carries no floating-point code
@@ -79,6 +91,8 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
                                                           size_t out_stride, int premultiplied) {
     constexpr int MAXQ = 16 * CH;
     __shared__ __align__(16) uint2 s_mat[MAXQ * kJPT];
+    constexpr bool KARA = (OFHE_BCONV_KARA != 0) && CH == 1 && kCPT == 1 && MODE == 0;
+    __shared__ __align__(8) int32_t s_md[KARA ? MAXQ * kJPT : 2];  // m1 - m0 of every matrix entry (Karatsuba)
     __shared__ uint64_t s_src[MAXQ * 3];  // q, w, ws
     __shared__ uint64_t s_dst[kJPT * 4];  // p, floor(2^128/p) hi, lo, (pad)
     in += blockIdx.z * in_stride;
@@ -87,6 +101,8 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
     for (uint32_t e = threadIdx.x; e < MAXQ * kJPT; e += kThreads) {
         const uint32_t i = e / kJPT, j = j0 + e % kJPT;
         s_mat[e] = (i < t.sizeQ && j < t.sizeP) ? t.mat[(size_t)i * t.sizeP + j] : make_uint2(0u, 0u);
+        if constexpr (KARA)
+            s_md[e] = (int32_t)s_mat[e].y - (int32_t)s_mat[e].x;
     }
     for (uint32_t i = threadIdx.x; i < MAXQ; i += kThreads) {
         const bool ok    = i < t.sizeQ;
@@ -106,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
     const uint32_t N   = r.N;
     const uint32_t rr0 = blockIdx.x * (kThreads * kCPT) + threadIdx.x;  // coefficient c of this thread: rr0 + c*kThreads
     uint32_t y0[kCPT][MAXQ], y1[kCPT][MAXQ];
+    int32_t yd[KARA ? MAXQ : 1];  // y1 - y0 (Karatsuba middle factor)
     double nu[kCPT];  // modes 1, 2: the floating-point overflow / rounding estimate, accumulated in index order with
                       // separately rounded multiply and add (no FMA contraction), exactly as the reference's loop
 #pragma unroll
@@ -123,6 +140,8 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
                 nu[c] = __dadd_rn(nu[c], __dmul_rn(__ull2double_rn(y), t.dbl[i]));
             y0[c][i] = (uint32_t)y & kMask30;
             y1[c][i] = (uint32_t)(y >> 30);
+            if constexpr (KARA)
+                yd[i] = (int32_t)y1[c][i] - (int32_t)y0[c][i];
         }
     }
     // the output-pair loop stays rolled: the fully unrolled body (64 KB of code) thrashed the instruction cache
@@ -141,6 +160,32 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
 #pragma unroll
                 for (int o = 0; o < 2; ++o)
                     a[c][o][0] = a[c][o][1] = a[c][o][2] = a[c][o][3] = 0;
+            if constexpr (KARA) {
+                // three products per MAC:  y*m = y0 m0 + y1 m1 2^60 + (y0 m0 + y1 m1 - (y1-y0)(m1-m0)) 2^30.
+                // a[.][0] = sum y0 m0, a[.][3] = sum y1 m1 (unsigned, < 2^64 for 16 terms); the signed middle products
+                // (|.| < 2^60) go to a[.][1] for i < 8 and a[.][2] for i >= 8, each within int64.
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint4 m  = *reinterpret_cast<const uint4*>(&s_mat[i * kJPT + j]);
+                    const int2 md  = *reinterpret_cast<const int2*>(&s_md[i * kJPT + j]);
+                    const int mid  = i < 8 ? 1 : 2;
+                    a[0][0][0]     = mad_wide(y0[0][i], m.x, a[0][0][0]);
+                    a[0][0][3]     = mad_wide(y1[0][i], m.y, a[0][0][3]);
+                    a[0][0][mid]   = (uint64_t)mad_wide_s(yd[i], md.x, (int64_t)a[0][0][mid]);
+                    a[0][1][0]     = mad_wide(y0[0][i], m.z, a[0][1][0]);
+                    a[0][1][3]     = mad_wide(y1[0][i], m.w, a[0][1][3]);
+                    a[0][1][mid]   = (uint64_t)mad_wide_s(yd[i], md.y, (int64_t)a[0][1][mid]);
+                }
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                    const uint64_t* a4 = a[0][o];
+                    // middle column = A + C - D (non-negative); D = D_a + D_b signed
+                    const unsigned __int128 mid = (unsigned __int128)a4[0] + a4[3] -
+                                                  (unsigned __int128)((__int128)(int64_t)a4[1] + (int64_t)a4[2]);
+                    total[0][o] += (unsigned __int128)a4[0] + (mid << 30) + (((unsigned __int128)a4[3]) << 60);
+                }
+                continue;
+            }
 #pragma unroll
             for (int i = 16 * ch; i < 16 * ch + 16; ++i) {
                 const uint4 m = *reinterpret_cast<const uint4*>(&s_mat[i * kJPT + j]);  // (lo,hi) of j and of j+1
