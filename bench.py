@@ -27,6 +27,10 @@ import time
 
 import numpy as np
 
+# several independent multiplications (and, with N > 1, their spinning device barriers) are in flight on separate
+# streams: give every stream its own hardware queue so that none is serialised behind another one's barrier kernel
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "openfhe-development_b200"))
 
