@@ -9,6 +9,10 @@ import sys
 import numpy as np
 import pytest
 
+# the virtual-rank tests keep up to eight streams with spinning device barriers in flight on one GPU: one hardware
+# queue per stream, so that no stream is serialised behind another one's barrier kernel (must be set before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "openfhe-development_b200"))
