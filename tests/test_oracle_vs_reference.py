@@ -125,3 +125,19 @@ def test_ckks_tables_and_keyswitch(oracle, reference, args):
     finally:
         oc.close()
         rc.close()
+
+
+@pytest.mark.parametrize("args", [(1 << 16, 44, 59, 60, 0, 0), (1 << 12, 3, 45, 55, 0, 1), (1 << 13, 11, 50, 60, 4, 2),
+                                  (1 << 11, 1, 30, 40, 0, 0), (1 << 12, 24, 59, 60, 3, 1)])
+def test_product_paramgen_matches_reference_chain(reference, args):
+    """The host-side chain generator of the library (ofhe_ckks_paramgen, csrc/hostmath.cpp) reproduces the moduli,
+    roots, P basis and digit shape the reference's CryptoParametersCKKSRNS picks -- including BASELINE config 2."""
+    import ofhe_b200
+
+    rc = reference.ckks(*args)
+    try:
+        p = ofhe_b200.ckks_paramgen(*args)
+        assert (p["N"], p["sizeQ"], p["sizeP"], p["dnum"], p["alpha"]) == (rc.N, rc.sizeQ, rc.sizeP, rc.dnum, rc.alpha)
+        assert (p["moduli"] == rc.moduli).all() and (p["roots"] == rc.roots).all()
+    finally:
+        rc.close()
