@@ -262,6 +262,13 @@ int ofhe_ipc_release(ofhe_ctx* ctx, void* dptr);
  *      ct*_d [2][sizeQ][N] EVALUATION.  norelin: out3_d [3][sizeQ][N] COEFFICIENT (the reference's cvMult).  With
  *      relinearisation: `hks` = HYBRID context over Q + P of the same crypto context, out_d [2][sizeQ][N] EVALUATION.   */
 typedef struct ofhe_bfv ofhe_bfv;
+/* The same tables from (Q, R, t) alone, for callers without a CryptoParametersBFVRNS at hand (host routine, word-size
+ * arithmetic; bfvrns-cryptoparameters.cpp:140-600).  which: 0 QlHatInvModq[sizeQ]  1 QlHatModr[sizeR][sizeQ]
+ * 2 alphaQlModr[sizeQ+1][sizeR]  3 qInv[sizeQ] (double)  4 negRlQlHatInvModq[sizeQ]  5 qInvModr[sizeQ][sizeR]
+ * 6 RlHatInvModr[sizeR]  7 RlHatModq[sizeQ][sizeR]  8 alphaRlModq[sizeR+1][sizeQ]  9 rInv[sizeR] (double)
+ * 10 tQlSlHatInvModsDivsModq[sizeQ][sizeR+1]  11 tQlSlHatInvModsDivsFrac[sizeR] (double); out_h needs room for the table */
+int ofhe_bfv_tables_host(uint32_t sizeQ, const uint64_t* moduliQ_h, uint32_t sizeR, const uint64_t* moduliR_h, uint64_t t,
+                         int which, void* out_h, size_t* count_out);
 int ofhe_bfv_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeR, const ofhe_bconv* q_to_r_exact,
                     const ofhe_bconv* q_to_r_approx, const ofhe_bconv* r_to_q_exact, const ofhe_bconv* scale_round,
                     ofhe_bfv** out);

@@ -907,6 +907,19 @@ int ofhe_ipc_release(ofhe_ctx* ctx, void* dptr) {
 struct ofhe_bfv {
     BfvMult* b;
 };
+int ofhe_bfv_tables_host(uint32_t sizeQ, const uint64_t* moduliQ_h, uint32_t sizeR, const uint64_t* moduliR_h, uint64_t t,
+                         int which, void* out_h, size_t* count_out) {
+    return guard([&] {
+        OFHE_REQUIRE(sizeQ >= 1 && sizeR >= 1 && sizeQ <= 64 && sizeR <= 64, "BFV basis sizes out of range");
+        for (uint32_t i = 0; i < sizeQ; ++i)
+            for (uint32_t j = 0; j < sizeR; ++j)
+                OFHE_REQUIRE(moduliQ_h[i] != moduliR_h[j], "Q and R must be disjoint");
+        const size_t n = hm::bfv_table(moduliQ_h, sizeQ, moduliR_h, sizeR, t, which, out_h);
+        OFHE_REQUIRE(n != 0, "unknown BFV table");
+        if (count_out)
+            *count_out = n;
+    });
+}
 int ofhe_bfv_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeR, const ofhe_bconv* q_to_r_exact,
                     const ofhe_bconv* q_to_r_approx, const ofhe_bconv* r_to_q_exact, const ofhe_bconv* scale_round,
                     ofhe_bfv** out) {

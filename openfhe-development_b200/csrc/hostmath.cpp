@@ -187,5 +187,84 @@ CkksChain ckks_chain(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t f
     return c;
 }
 
+size_t bfv_table(const uint64_t* Q, uint32_t nQ, const uint64_t* R, uint32_t nR, uint64_t t, int which, void* out) {
+    uint64_t* u = static_cast<uint64_t*>(out);
+    double* d   = static_cast<double*>(out);
+    // (QR / m)^-1 mod m for a modulus m that is Q[skipQ] or R[skipR]
+    auto qr_hat_inv = [&](long skipQ, long skipR, uint64_t m) {
+        return inv(mul(prod_mod(Q, nQ, skipQ, m), prod_mod(R, nR, skipR, m), m), m);
+    };
+    switch (which) {
+        case 0:  // (Q/q_i)^-1 mod q_i                                                         :181-191
+            for (uint32_t i = 0; i < nQ; ++i)
+                u[i] = inv(prod_mod(Q, nQ, (long)i, Q[i]), Q[i]);
+            return nQ;
+        case 1:  // (Q/q_i) mod r_j, [j][i]                                                     :194-202
+            for (uint32_t j = 0; j < nR; ++j)
+                for (uint32_t i = 0; i < nQ; ++i)
+                    u[(size_t)j * nQ + i] = prod_mod(Q, nQ, (long)i, R[j]);
+            return (size_t)nQ * nR;
+        case 2:  // k * Q mod r_j, [k][j], k = 0..sizeQ                                         :336-355
+            for (uint32_t k = 0; k <= nQ; ++k)
+                for (uint32_t j = 0; j < nR; ++j)
+                    u[(size_t)k * nR + j] = mul(prod_mod(Q, nQ, -1, R[j]), k, R[j]);
+            return (size_t)(nQ + 1) * nR;
+        case 3:  // 1 / q_i in double                                                           :262-265
+            for (uint32_t i = 0; i < nQ; ++i)
+                d[i] = 1. / static_cast<double>(Q[i]);
+            return nQ;
+        case 4:  // q_i - R * (Q/q_i)^-1 mod q_i                                                :506-521
+            for (uint32_t i = 0; i < nQ; ++i) {
+                const uint64_t q = Q[i];
+                u[i] = q - mul(prod_mod(R, nR, -1, q), inv(prod_mod(Q, nQ, (long)i, q), q), q);
+            }
+            return nQ;
+        case 5:  // q_i^-1 mod r_j, [i][j]                                                      :524-530
+            for (uint32_t i = 0; i < nQ; ++i)
+                for (uint32_t j = 0; j < nR; ++j)
+                    u[(size_t)i * nR + j] = inv(Q[i] % R[j], R[j]);
+            return (size_t)nQ * nR;
+        case 6:  // (R/r_j)^-1 mod r_j                                                          :361-370
+            for (uint32_t j = 0; j < nR; ++j)
+                u[j] = inv(prod_mod(R, nR, (long)j, R[j]), R[j]);
+            return nR;
+        case 7:  // (R/r_j) mod q_i, [i][j]                                                     :372-400
+            for (uint32_t i = 0; i < nQ; ++i)
+                for (uint32_t j = 0; j < nR; ++j)
+                    u[(size_t)i * nR + j] = prod_mod(R, nR, (long)j, Q[i]);
+            return (size_t)nQ * nR;
+        case 8:  // k * R mod q_i, [k][i], k = 0..sizeR                                         :402-425
+            for (uint32_t k = 0; k <= nR; ++k)
+                for (uint32_t i = 0; i < nQ; ++i)
+                    u[(size_t)k * nQ + i] = mul(prod_mod(R, nR, -1, Q[i]), k, Q[i]);
+            return (size_t)(nR + 1) * nQ;
+        case 9:  // 1 / r_j in double                                                           :429-432
+            for (uint32_t j = 0; j < nR; ++j)
+                d[j] = 1. / static_cast<double>(R[j]);
+            return nR;
+        case 10:  // floor(t Q (QR/s)^-1 / s) mod q_i, s = r_j (j < sizeR) or q_i (last column), [i][sizeR+1]   :565-593
+            for (uint32_t i = 0; i < nQ; ++i) {
+                const uint64_t q = Q[i];
+                for (uint32_t j = 0; j < nR; ++j) {
+                    // X = t Q c with c = (QR/r_j)^-1 mod r_j; X = r_j D + rem and q_i | X, so D = -rem / r_j (mod q_i)
+                    const uint64_t r   = R[j];
+                    const uint64_t rem = mul(mul(t % r, prod_mod(Q, nQ, -1, r), r), qr_hat_inv(-1, (long)j, r), r);
+                    u[(size_t)i * (nR + 1) + j] = mul((q - rem % q) % q, inv(r % q, q), q);
+                }
+                // s = q_i divides Q: the quotient is exact, t (Q/q_i) c mod q_i
+                u[(size_t)i * (nR + 1) + nR] = mul(mul(t % q, prod_mod(Q, nQ, (long)i, q), q), qr_hat_inv((long)i, -1, q), q);
+            }
+            return (size_t)nQ * (nR + 1);
+        case 11:  // ((t Q (QR/r_j)^-1) mod r_j) / r_j, both converted to double first             :569-577
+            for (uint32_t j = 0; j < nR; ++j) {
+                const uint64_t r   = R[j];
+                const uint64_t rem = mul(mul(t % r, prod_mod(Q, nQ, -1, r), r), qr_hat_inv(-1, (long)j, r), r);
+                d[j]               = static_cast<double>(rem) / static_cast<double>(r);
+            }
+            return nR;
+        default: return 0;
+    }
+}
+
 }  // namespace hm
 }  // namespace ofhe

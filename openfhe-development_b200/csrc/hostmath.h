@@ -63,5 +63,15 @@ struct CkksChain {
 CkksChain ckks_chain(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
                      int scal_tech);
 
+// BFV (HPSPOVERQ) multiplication tables at the full level, from (Q, R, t) alone -- the quantities
+// CryptoParametersBFVRNS::PrecomputeCRTTables forms with BigInteger (pke/lib/scheme/bfvrns/bfvrns-cryptoparameters.cpp:140-600),
+// here with word-size modular arithmetic only.  `which` and the layouts follow the getters:
+//   0 QlHatInvModq[sizeQ]            1 QlHatModr[sizeR][sizeQ]       2 alphaQlModr[sizeQ+1][sizeR]   3 qInv[sizeQ] (double)
+//   4 negRlQlHatInvModq[sizeQ]       5 qInvModr[sizeQ][sizeR]        6 RlHatInvModr[sizeR]           7 RlHatModq[sizeQ][sizeR]
+//   8 alphaRlModq[sizeR+1][sizeQ]    9 rInv[sizeR] (double)         10 tQlSlHatInvModsDivsModq[sizeQ][sizeR+1]
+//  11 tQlSlHatInvModsDivsFrac[sizeR] (double)
+// Returns the number of elements written (uint64_t or double, by table), 0 for an unknown table.
+size_t bfv_table(const uint64_t* Q, uint32_t sizeQ, const uint64_t* R, uint32_t sizeR, uint64_t t, int which, void* out);
+
 }  // namespace hm
 }  // namespace ofhe

@@ -81,6 +81,7 @@ SIGNATURES = {
     "ofhe_shard_evalmult_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_b": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_c": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_bfv_tables_host": (C.c_int, [C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint64, C.c_int, _vp, C.POINTER(C.c_size_t)]),
     "ofhe_bfv_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "ofhe_bfv_destroy": (None, [_vp]),
     "ofhe_bfv_evalmult_norelin": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
@@ -355,6 +356,27 @@ class BaseConv:
             self.h = None
 
 
+BFV_TABLE_NAMES = ["QlHatInvModq", "QlHatModr", "alphaQlModr", "qInv", "mNegRlQlHatInvModq", "qInvModr", "RlHatInvModr",
+                   "RlHatModq", "alphaRlModq", "rInv", "tQlSlHatInvModsDivsModq", "tQlSlHatInvModsDivsFrac"]
+
+
+def bfv_tables(moduliQ, moduliR, t):
+    """HPSPOVERQ multiplication tables at the full level from (Q, R, t) alone (host arithmetic, no GPU needed)."""
+    Q = np.ascontiguousarray(moduliQ, dtype=np.uint64)
+    R = np.ascontiguousarray(moduliR, dtype=np.uint64)
+    nQ, nR = len(Q), len(R)
+    shapes = [(nQ,), (nR, nQ), (nQ + 1, nR), (nQ,), (nQ,), (nQ, nR), (nR,), (nQ, nR), (nR + 1, nQ), (nR,), (nQ, nR + 1),
+              (nR,)]
+    out = {}
+    for w, (name, shp) in enumerate(zip(BFV_TABLE_NAMES, shapes)):
+        a = np.empty(shp, dtype=np.float64 if w in (3, 9, 11) else np.uint64)
+        n = C.c_size_t(0)
+        _ck(lib().ofhe_bfv_tables_host(nQ, Q.ctypes.data, nR, R.ctypes.data, int(t), w, a.ctypes.data, C.byref(n)))
+        assert n.value == a.size
+        out[name] = a
+    return out
+
+
 class BfvMult:
     """BFV EvalMult, HPSPOVERQ (LeveledSHEBFVRNS::EvalMult): `ring` registers Q then R; `T` holds the reference's
     CryptoParametersBFVRNS tables at level sizeQ-1 under the getter names without the `Get` prefix."""
@@ -372,6 +394,11 @@ class BfvMult:
         h = _vp()
         _ck(lib().ofhe_bfv_create(ring.h, sizeQ, sizeR, *[c.h for c in self.convs], C.byref(h)))
         self.h = h
+
+    @classmethod
+    def from_moduli(cls, ring, sizeQ, sizeR, t):
+        """Tables derived by the library itself from the ring's moduli (Q then R) and the plaintext modulus t."""
+        return cls(ring, sizeQ, sizeR, bfv_tables(ring.moduli[:sizeQ], ring.moduli[sizeQ:sizeQ + sizeR], t))
 
     def close(self):
         if self.h:
