@@ -23,6 +23,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # no test may hang the tier: device barriers give up after ~2 s each, everything else is bounded by this
+    if config.pluginmanager.hasplugin("timeout"):
+        for it in items:
+            if it.get_closest_marker("timeout") is None:
+                it.add_marker(pytest.mark.timeout(900))
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle_lib import Oracle
