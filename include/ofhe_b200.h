@@ -277,6 +277,20 @@ int ofhe_bfv_evalmult_norelin(ofhe_bfv* b, const uint64_t* ct1_d, const uint64_t
 int ofhe_bfv_evalmult(ofhe_bfv* b, ofhe_hks* hks, const uint64_t* ct1_d, const uint64_t* ct2_d, const ofhe_evk* evk,
                       uint64_t* out_d, void* stream);
 
+/* ---- the reference's wire / on-disk format: cereal portable-binary archives of a DCRTPoly as written by
+ *      Serial::Serialize(poly, stream, SerType::BINARY) -- DCRTPolyImpl::save dcrtpoly.h:337-341, PolyImpl::save
+ *      poly.h:336-340, NativeVectorT::save mubintvecnat.h:656-665, ElemParams::save elemparams.h:229-236.
+ *      scan : shape_out = (N, n_towers, format 0 EVALUATION / 1 COEFFICIENT); per tower its modulus, root of unity and
+ *             the byte offset of its N raw words inside the buffer (any output array may be NULL).
+ *      write: the byte-identical archive for [n_towers][N] host words (what the reference's Deserialize expects).
+ *      upload: scan + one asynchronous host-to-device copy per tower, archive -> dst_d [n_towers][N] (no host DCRTPoly). */
+int ofhe_cereal_dcrtpoly_scan(const void* buf_h, size_t len, uint32_t max_towers, uint32_t* shape_out,
+                              uint64_t* moduli_out, uint64_t* roots_out, size_t* offsets_out);
+int ofhe_cereal_dcrtpoly_write(uint32_t N, uint32_t n_towers, const uint64_t* moduli_h, const uint64_t* roots_h,
+                               uint32_t format, const uint64_t* data_h, void* out_h, size_t cap, size_t* written_out);
+int ofhe_dcrtpoly_upload_cereal(ofhe_ctx* ctx, const void* buf_h, size_t len, uint32_t max_towers, uint64_t* dst_d,
+                                uint32_t* shape_out, void* stream);
+
 /* fills dst_d [n_limbs][N] with uniform residues in [0, q_l) from a counter-based generator (synthetic inputs) */
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,
                       void* stream);

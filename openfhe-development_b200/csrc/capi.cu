@@ -6,6 +6,7 @@
 #include "hks.h"
 #include "hostmath.h"
 #include "bfv.h"
+#include "cereal_io.h"
 #include "shard.h"
 
 using namespace ofhe;
@@ -954,6 +955,51 @@ int ofhe_bfv_evalmult(ofhe_bfv* b, ofhe_hks* hks, const uint64_t* ct1_d, const u
     return guard([&] {
         use(b->b->ring);
         b->b->evalmult(*hks->h, ct1_d, ct2_d, *evk->k, out_d, S(stream));
+    });
+}
+
+// ---- the reference's wire format for DCRTPoly (cereal portable binary), see cereal_io.cpp
+int ofhe_cereal_dcrtpoly_scan(const void* buf_h, size_t len, uint32_t max_towers, uint32_t* shape_out,
+                              uint64_t* moduli_out, uint64_t* roots_out, size_t* offsets_out) {
+    return guard([&] {
+        std::vector<uint64_t> q, r;
+        std::vector<size_t> off;
+        const cio::DcrtInfo info = cio::scan_dcrtpoly(buf_h, len, &q, &r, &off);
+        OFHE_REQUIRE(info.n_towers <= max_towers, "serialized polynomial has more towers than the caller allowed for");
+        shape_out[0] = info.N, shape_out[1] = info.n_towers, shape_out[2] = info.format;
+        for (uint32_t t = 0; t < info.n_towers; ++t) {
+            if (moduli_out)
+                moduli_out[t] = q[t];
+            if (roots_out)
+                roots_out[t] = r[t];
+            if (offsets_out)
+                offsets_out[t] = off[t];
+        }
+    });
+}
+int ofhe_cereal_dcrtpoly_write(uint32_t N, uint32_t n_towers, const uint64_t* moduli_h, const uint64_t* roots_h,
+                               uint32_t format, const uint64_t* data_h, void* out_h, size_t cap, size_t* written_out) {
+    return guard([&] {
+        std::vector<uint8_t> bytes;
+        cio::write_dcrtpoly(N, n_towers, moduli_h, roots_h, format, data_h, bytes);
+        *written_out = bytes.size();  // reported even when `cap` is too small, so the caller can size the buffer
+        OFHE_REQUIRE(bytes.size() <= cap, "output buffer too small for the serialized polynomial");
+        std::memcpy(out_h, bytes.data(), bytes.size());
+    });
+}
+int ofhe_dcrtpoly_upload_cereal(ofhe_ctx* ctx, const void* buf_h, size_t len, uint32_t max_towers, uint64_t* dst_d,
+                                uint32_t* shape_out, void* stream) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        std::vector<size_t> off;
+        const cio::DcrtInfo info = cio::scan_dcrtpoly(buf_h, len, nullptr, nullptr, &off);
+        OFHE_REQUIRE(info.n_towers <= max_towers, "serialized polynomial has more towers than the destination slab");
+        if (shape_out)
+            shape_out[0] = info.N, shape_out[1] = info.n_towers, shape_out[2] = info.format;
+        // every tower payload is N raw little-endian words: straight from the (ideally pinned) archive to its device row
+        for (uint32_t t = 0; t < info.n_towers; ++t)
+            OFHE_CUDA(cudaMemcpyAsync(dst_d + (size_t)t * info.N, static_cast<const uint8_t*>(buf_h) + off[t],
+                                      sizeof(uint64_t) * info.N, cudaMemcpyHostToDevice, S(stream)));
     });
 }
 

@@ -81,6 +81,10 @@ SIGNATURES = {
     "ofhe_shard_evalmult_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_b": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_c": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_cereal_dcrtpoly_scan": (C.c_int, [_vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_cereal_dcrtpoly_write": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t,
+                                             C.POINTER(C.c_size_t)]),
+    "ofhe_dcrtpoly_upload_cereal": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp]),
     "ofhe_bfv_tables_host": (C.c_int, [C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint64, C.c_int, _vp, C.POINTER(C.c_size_t)]),
     "ofhe_bfv_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "ofhe_bfv_destroy": (None, [_vp]),
@@ -354,6 +358,32 @@ class BaseConv:
         if self.h:
             lib().ofhe_bconv_destroy(self.h)
             self.h = None
+
+
+def cereal_scan_dcrtpoly(buf, max_towers=256):
+    """Serialized DCRTPoly (bytes-like) -> dict(N, n_towers, format, moduli, roots, offsets): host parsing only."""
+    b = np.frombuffer(buf, dtype=np.uint8)
+    shape = np.zeros(3, dtype=np.uint32)
+    q, r = np.zeros(max_towers, dtype=np.uint64), np.zeros(max_towers, dtype=np.uint64)
+    off = np.zeros(max_towers, dtype=np.uintp)
+    _ck(lib().ofhe_cereal_dcrtpoly_scan(b.ctypes.data, b.size, max_towers, shape.ctypes.data, q.ctypes.data,
+                                        r.ctypes.data, off.ctypes.data))
+    n = int(shape[1])
+    return dict(N=int(shape[0]), n_towers=n, format=int(shape[2]), moduli=q[:n].copy(), roots=r[:n].copy(),
+                offsets=off[:n].astype(np.int64))
+
+
+def cereal_write_dcrtpoly(moduli, roots, fmt, data):
+    """[n_towers][N] uint64 residues -> the reference's portable-binary archive (bytes)."""
+    q = np.ascontiguousarray(moduli, dtype=np.uint64)
+    r = np.ascontiguousarray(roots, dtype=np.uint64)
+    d = np.ascontiguousarray(data, dtype=np.uint64)
+    L, N = d.shape
+    out = np.empty(L * (8 * N + 128) + 64 * L + 256, dtype=np.uint8)
+    n = C.c_size_t(0)
+    _ck(lib().ofhe_cereal_dcrtpoly_write(N, L, q.ctypes.data, r.ctypes.data, int(fmt), d.ctypes.data, out.ctypes.data,
+                                         out.size, C.byref(n)))
+    return out[:n.value].tobytes()
 
 
 BFV_TABLE_NAMES = ["QlHatInvModq", "QlHatModr", "alphaQlModr", "qInv", "mNegRlQlHatInvModq", "qInvModr", "RlHatInvModr",

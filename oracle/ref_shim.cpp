@@ -19,6 +19,13 @@
 #include <vector>
 
 #include "openfhe.h"
+#include <sstream>
+
+// serialisation of the lattice layer (cereal): DCRTPoly / key objects to portable-binary and JSON
+#include "ciphertext-ser.h"
+#include "cryptocontext-ser.h"
+#include "key/key-ser.h"
+#include "scheme/ckksrns/ckksrns-ser.h"
 #include "utils/utilities-int.h"
 
 using namespace lbcrypto;
@@ -250,6 +257,27 @@ int ref_dcrt_switch_format(uint32_t N, uint32_t L, const uint64_t* moduli, const
         A.SwitchFormat();
         dump_poly(A, data);
     });
+}
+// Serial::Serialize(DCRTPoly, BINARY / JSON) of a poly built from caller-supplied residues: returns the byte count
+// (0 on failure, or if `cap` is too small); format EVALUATION if eval != 0.   dcrtpoly.h:337-351, mubintvecnat.h:656-705
+size_t ref_dcrt_serialize(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, int eval,
+                          const uint64_t* data, int json, uint8_t* out, size_t cap) {
+    size_t n = 0;
+    guarded([&] {
+        auto params = make_params(N, L, moduli, roots);
+        DCRTPoly A  = make_poly(params, eval ? Format::EVALUATION : Format::COEFFICIENT, data);
+        std::stringstream ss;
+        if (json)
+            Serial::Serialize(A, ss, SerType::JSON);
+        else
+            Serial::Serialize(A, ss, SerType::BINARY);
+        std::string b = ss.str();
+        if (b.size() <= cap) {
+            std::memcpy(out, b.data(), b.size());
+            n = b.size();
+        }
+    });
+    return n;
 }
 int ref_dcrt_automorphism(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, uint32_t k,
                           const uint64_t* a, uint64_t* out) {

@@ -372,6 +372,8 @@ class Reference:
         _sig(L, "ref_dcrt_binop", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_int, u64p, u64p, u64p)
         _sig(L, "ref_dcrt_times_scalars", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, u64p, u64p, u64p)
         _sig(L, "ref_dcrt_switch_format", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_int, u64p)
+        _sig(L, "ref_dcrt_serialize", C.c_size_t, C.c_uint32, C.c_uint32, u64p, u64p, C.c_int, u64p, C.c_int,
+             C.c_void_p, C.c_size_t)
         _sig(L, "ref_dcrt_automorphism", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p)
         _sig(L, "ref_automorphism_map", C.c_int, C.c_uint32, C.c_uint32, u32p)
         _sig(L, "ref_switch_modulus", C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, u64p)
@@ -440,6 +442,18 @@ class Reference:
         self._ok(self.L.ref_dcrt_switch_format(d.shape[1], d.shape[0], np.ascontiguousarray(moduli),
                                                np.ascontiguousarray(roots), int(from_eval), d))
         return d
+
+    def dcrt_serialize(self, moduli, roots, evaluation, data, json=False):
+        """Serial::Serialize(DCRTPoly, BINARY | JSON) of a polynomial with these towers -> bytes."""
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        L, N = data.shape
+        buf = np.zeros(L * (N * (24 if json else 8) + 1024) + 8192, dtype=np.uint8)
+        n = self.L.ref_dcrt_serialize(N, L, np.ascontiguousarray(moduli, dtype=np.uint64),
+                                      np.ascontiguousarray(roots, dtype=np.uint64), int(evaluation), data, int(json),
+                                      buf.ctypes.data, buf.size)
+        if n == 0:
+            raise RuntimeError(self.L.ref_last_error().decode() or "serialization failed")
+        return buf[:n].tobytes()
 
     def dcrt_binop(self, moduli, roots, op, a, b=None):
         out = np.empty_like(a)
