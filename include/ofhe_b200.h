@@ -190,7 +190,7 @@ int ofhe_hks_keyswitch_ext(ofhe_hks* hks, uint32_t sizeQl, int add_first, const 
 
 /* ---- a20 (host helper, setup time) CKKS modulus chain + auxiliary primes with the reference's selection rules
  *      ParameterGenerationCKKSRNS::SinglePrimeModuliGen  pke/lib/scheme/ckksrns/ckksrns-parametergeneration.cpp:409-518
- *      scal_tech: 0 FIXEDMANUAL 1 FIXEDAUTO 2 FLEXIBLEAUTO.  shape_out: sizeQ, sizeP, dnum, alpha.
+ *      scal_tech: 0 FIXEDMANUAL 1 FIXEDAUTO 2 FLEXIBLEAUTO 3 FLEXIBLEAUTOEXT (sizeQ = depth + 2).  shape_out: sizeQ, sizeP, dnum, alpha.
  *      moduli_out / roots_out need room for (depth + 1) + 64 words.                                                */
 int ofhe_ckks_paramgen(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
                        int scal_tech, uint64_t* moduli_out, uint64_t* roots_out, uint32_t* shape_out);

@@ -112,15 +112,19 @@ uint32_t product_bits(const uint64_t* v, size_t n) {
 
 CkksChain ckks_chain(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
                      int scal_tech) {
-    if (scal_tech < 0 || scal_tech > 2)
-        throw std::runtime_error("ckks_chain: scaling technique must be FIXEDMANUAL(0), FIXEDAUTO(1) or FLEXIBLEAUTO(2)");
+    if (scal_tech < 0 || scal_tech > 3)
+        throw std::runtime_error(
+            "ckks_chain: scaling technique must be FIXEDMANUAL(0), FIXEDAUTO(1), FLEXIBLEAUTO(2) or FLEXIBLEAUTOEXT(3)");
+    const bool ext = scal_tech == 3;  // FLEXIBLEAUTOEXT = the FLEXIBLEAUTO chain plus one extra 20-bit-class modulus
+    if (ext)
+        scal_tech = 2;
     CkksChain c;
     c.N     = N;
     c.sizeQ = depth + 1;
     if (dnum == 0)  // scheme-utils.h:35-43
         dnum = depth > 3 ? 3 : (depth > 0 ? 2 : 1);
     const uint64_t m = 2 * (uint64_t)N;
-    const uint32_t L = c.sizeQ;
+    uint32_t L = c.sizeQ;
     std::vector<uint64_t> Q(L);
     Q[L - 1]    = first_prime(scale_bits, m);
     uint64_t hi = Q[L - 1];
@@ -159,7 +163,16 @@ CkksChain ckks_chain(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t f
         if (std::find(Q.begin() + 1, Q.end(), Q[0]) != Q.end())
             Q[0] = next_prime(hi, m);
     }
+    if (ext) {  // ckksrns-parametergeneration.cpp:518-529, DEFAULT_EXTRA_MOD_SIZE = 20 (rns-modulus-limits.h:42)
+        hi            = std::max(hi, Q[0]);
+        uint64_t cand = first_prime(20 - 1, m);
+        if (std::find(Q.begin(), Q.end(), cand) != Q.end())
+            cand = next_prime(hi, m);
+        Q.push_back(cand);
+        c.sizeQ += 1;
+    }
     // digits and auxiliary basis
+    L       = c.sizeQ;
     c.dnum  = dnum;
     c.alpha = (L + dnum - 1) / dnum;
     if (L <= c.alpha * (dnum - 1))

@@ -414,6 +414,10 @@ static uint64_t prod_mod(const uint64_t* v, uint32_t n, int skip, uint64_t m) {
 /* ckksrns-parametergeneration.cpp:409-518 SinglePrimeModuliGen */
 static void ckks_moduli_q(uint32_t N, uint32_t numPrimes, uint32_t scaleBits, uint32_t firstBits, int scalTech,
                           uint64_t* mq) {
+    /* scalTech 3 = FLEXIBLEAUTOEXT: the FLEXIBLEAUTO chain, then one extra modulus written to mq[numPrimes] */
+    const int ext = scalTech == 3;
+    if (ext)
+        scalTech = 2;
     uint64_t m = 2 * (uint64_t)N;
     uint64_t q = orc_first_prime(scaleBits, m);
     mq[numPrimes - 1] = q;
@@ -488,6 +492,17 @@ static void ckks_moduli_q(uint32_t N, uint32_t numPrimes, uint32_t scaleBits, ui
                 break;
             }
     }
+    if (ext) { /* :518-529, DEFAULT_EXTRA_MOD_SIZE = 20 (rns-modulus-limits.h:42) */
+        if (mq[0] > maxPrime)
+            maxPrime = mq[0];
+        uint64_t t = orc_first_prime(20 - 1, m);
+        for (uint32_t i = 0; i < numPrimes; ++i)
+            if (mq[i] == t) {
+                t = orc_next_prime(maxPrime, m);
+                break;
+            }
+        mq[numPrimes] = t;
+    }
 }
 
 static uint32_t bitlen_prod(const uint64_t* v, uint32_t n) { /* exact bit length of a product of u64 */
@@ -518,6 +533,8 @@ orc_ckks* orc_ckks_create(uint32_t N, uint32_t depth, uint32_t scaleBits, uint32
         dnum = depth > 3 ? 3 : (depth > 0 ? 2 : 1);
     uint64_t mq[256];
     ckks_moduli_q(N, sizeQ, scaleBits, firstBits, scalTech, mq);
+    if (scalTech == 3) /* ckksrns-parametergeneration.cpp:169: the vector holds numPrimes + 1 moduli */
+        sizeQ += 1;
     /* rns-cryptoparameters.cpp:86-97 numPerPartQ; :130-148 sizeP from the widest digit, auxBits = 60 */
     uint32_t alpha = (sizeQ + dnum - 1) / dnum;
     uint32_t maxBits = 0;

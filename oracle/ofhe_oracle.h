@@ -60,7 +60,7 @@ void orc_scale_and_round(uint32_t N, uint32_t sizeI, uint32_t sizeO, const uint6
 
 /* a20 CKKS / HYBRID tables */
 typedef struct orc_ckks orc_ckks;
-/* scal_tech: 0 FIXEDMANUAL, 1 FIXEDAUTO, 2 FLEXIBLEAUTO (FLEXIBLEAUTOEXT not restated) */
+/* scal_tech: 0 FIXEDMANUAL, 1 FIXEDAUTO, 2 FLEXIBLEAUTO, 3 FLEXIBLEAUTOEXT (chain and tables; sizeQ = depth + 2) */
 orc_ckks* orc_ckks_create(uint32_t N, uint32_t depth, uint32_t scale_bits, uint32_t first_bits, uint32_t dnum,
                           int scal_tech);
 /* hybrid key-switch context over a caller-supplied chain (e.g. BFV's Q then P) */

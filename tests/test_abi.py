@@ -56,7 +56,8 @@ def test_host_number_theory_matches_oracle(oracle):
 
 
 @pytest.mark.parametrize("args", [(64, 4, 40, 50, 2, 0), (128, 5, 45, 55, 3, 2), (1 << 10, 6, 59, 60, 3, 1),
-                                  (1 << 9, 1, 45, 50, 0, 0), (1 << 12, 12, 50, 60, 0, 2)])
+                                  (1 << 9, 1, 45, 50, 0, 0), (1 << 12, 12, 50, 60, 0, 2), (1 << 11, 7, 50, 60, 0, 3),
+                                  (256, 3, 40, 50, 2, 3)])
 def test_ckks_paramgen_matches_oracle(oracle, args):
     p = ofhe_b200.ckks_paramgen(*args)
     c = oracle.ckks(*args)
@@ -102,6 +103,6 @@ def test_find_automorphism_index():
 
 def test_paramgen_errors_are_reported_not_thrown():
     with pytest.raises(ofhe_b200.OfheError):
-        ofhe_b200.ckks_paramgen(64, 4, 40, 50, 2, 3)  # FLEXIBLEAUTOEXT is not restated
+        ofhe_b200.ckks_paramgen(64, 4, 40, 50, 2, 4)  # COMPOSITESCALING* are not restated
     with pytest.raises(ofhe_b200.OfheError):
         ofhe_b200.ckks_paramgen(64, 4, 40, 50, 4, 0)  # 5 towers cannot fill 4 digits of ceil(5/4) = 2 (rns-cryptoparameters.cpp:87-93)

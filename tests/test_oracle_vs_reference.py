@@ -67,7 +67,7 @@ def test_limb_ops(oracle, reference):
 
 
 @pytest.mark.parametrize("args", [(1 << 10, 5, 50, 60, 0, 0), (1 << 11, 7, 40, 50, 2, 1), (1 << 10, 6, 59, 60, 3, 2),
-                                  (1 << 9, 1, 45, 50, 0, 0)])
+                                  (1 << 9, 1, 45, 50, 0, 0), (1 << 10, 4, 45, 55, 0, 3)])
 def test_ckks_tables_and_keyswitch(oracle, reference, args):
     N = args[0]
     oc, rc = oracle.ckks(*args), reference.ckks(*args)
@@ -102,12 +102,16 @@ def test_ckks_tables_and_keyswitch(oracle, reference, args):
             assert (k1[0] == k2[0]).all() and (k1[1] == k2[1]).all()
             ct1 = np.stack([seeded_residues(11, oc.moduli[:sizeQl], N), seeded_residues(12, oc.moduli[:sizeQl], N)])
             ct2 = np.stack([seeded_residues(13, oc.moduli[:sizeQl], N), seeded_residues(14, oc.moduli[:sizeQl], N)])
+            if args[5] == 3:
+                # FLEXIBLEAUTOEXT: cc->EvalMult / Rescale / EvalRotate first adjust levels (the extra modulus is dropped
+                # by scheme-level logic, out of scope); the DCRTPoly-level stages above are what the path replaces
+                continue
             assert (oc.evalmult(sizeQl, ct1, ct2, ea, eb) == rc.evalmult(sizeQl, ct1, ct2)).all()
             if sizeQl > 1:
                 assert (oc.rescale_poly(sizeQl, c) == rc.rescale_poly(sizeQl, c)).all()
                 r2 = rc.rescale(sizeQl, ct1)
                 assert (oc.rescale_poly(sizeQl, ct1[0]) == r2[0]).all()
-        for index in (1, -2):
+        for index in (() if args[5] == 3 else (1, -2)):
             k, ra, rb = rc.rotate_key(index)
             sizeQl = oc.sizeQ
             ct = np.stack([seeded_residues(21, oc.moduli[:sizeQl], N), seeded_residues(22, oc.moduli[:sizeQl], N)])
@@ -128,7 +132,8 @@ def test_ckks_tables_and_keyswitch(oracle, reference, args):
 
 
 @pytest.mark.parametrize("args", [(1 << 16, 44, 59, 60, 0, 0), (1 << 12, 3, 45, 55, 0, 1), (1 << 13, 11, 50, 60, 4, 2),
-                                  (1 << 11, 1, 30, 40, 0, 0), (1 << 12, 24, 59, 60, 3, 1)])
+                                  (1 << 11, 1, 30, 40, 0, 0), (1 << 12, 24, 59, 60, 3, 1), (1 << 12, 5, 50, 60, 0, 3),
+                                  (1 << 16, 44, 59, 60, 0, 3), (1 << 11, 2, 40, 50, 2, 3)])
 def test_product_paramgen_matches_reference_chain(reference, args):
     """The host-side chain generator of the library (ofhe_ckks_paramgen, csrc/hostmath.cpp) reproduces the moduli,
     roots, P basis and digit shape the reference's CryptoParametersCKKSRNS picks -- including BASELINE config 2."""
