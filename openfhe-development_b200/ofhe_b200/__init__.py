@@ -217,6 +217,18 @@ class Context:
     def download(t):
         return t.detach().cpu().numpy().view(np.uint64)
 
+    def upload_cereal(self, buf, max_towers=256):
+        """Serialized DCRTPoly (the reference's portable-binary archive) -> ([n_towers][N] device slab, scan info).
+        Pass a pinned buffer (e.g. a torch uint8 tensor from pin_memory()) for truly asynchronous copies."""
+        import torch
+
+        info = cereal_scan_dcrtpoly(buf if not hasattr(buf, "numpy") else buf.numpy(), max_towers)
+        dst = self.zeros(info["n_towers"], info["N"])
+        b = buf.numpy() if hasattr(buf, "numpy") else np.frombuffer(buf, dtype=np.uint8)
+        _ck(lib().ofhe_dcrtpoly_upload_cereal(self.h, b.ctypes.data, b.size, max_towers, _ptr(dst), None, _stream()))
+        torch.cuda.current_stream().synchronize()  # `b` may be a temporary view of the caller's bytes
+        return dst, info
+
     # raw cudaMalloc buffers (zero-filled) for the peer-push exchange: IPC handles exist only for whole allocations
     def raw_zeros(self, words):
         p = _vp()
