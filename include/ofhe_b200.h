@@ -237,7 +237,7 @@ int ofhe_shard_evalmult_b_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* e
                                uint64_t* const* gatherQ_of_rank_h, uint64_t* const* gatherP_of_rank_h, void* stream);
 /* flags buffers: ofhe_peer_flags_words(world, n_barriers) zero-initialised words per rank.  The kernel bumps this
  * rank's epoch for barrier `index`, publishes it to every rank (release, system scope) and waits until every rank's
- * arrival for that epoch is visible (acquire).  A wait longer than ~2 s gives up and counts a timeout (readable with
+ * arrival for that epoch is visible (acquire).  A wait longer than ~10 s gives up and counts a timeout (readable with
  * ofhe_peer_barrier_timeouts) instead of hanging the GPU.                                                            */
 size_t ofhe_peer_flags_words(uint32_t world, uint32_t n_barriers);
 int ofhe_peer_barrier(ofhe_ctx* ctx, uint64_t* const* flags_of_rank_h, uint32_t world, uint32_t rank, uint32_t index,

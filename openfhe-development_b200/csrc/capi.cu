@@ -827,7 +827,7 @@ __global__ void peer_barrier_kernel(PeerFlags pf, uint32_t world, uint32_t rank,
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
             if (seen >= epoch)
                 break;
-            if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz: give up rather than hang the device
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz: give up rather than hang the device
                 atomicAdd(reinterpret_cast<unsigned long long*>(mine + world + 1), 1ULL);
                 break;
             }

@@ -24,7 +24,7 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    # no test may hang the tier: device barriers give up after ~2 s each, everything else is bounded by this
+    # no test may hang the tier: device barriers give up after ~10 s each, everything else is bounded by this
     if config.pluginmanager.hasplugin("timeout"):
         for it in items:
             if it.get_closest_marker("timeout") is None:
