@@ -84,20 +84,37 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
-def cpu_reference_run(steps, warmup, threads=None):
-    """Times cc->EvalMult of the unmodified reference (oracle/_ref) on the workload, or the C oracle port."""
+def host_topology():
+    """(logical CPUs this process may use, physical cores among them)."""
+    cpus = sorted(os.sched_getaffinity(0))
+    cores = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/physical_package_id") as f:
+                pkg = f.read().strip()
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/core_id") as f:
+                cores.add((pkg, f.read().strip()))
+        except OSError:
+            cores.add(("?", str(c)))
+    return len(cpus), max(1, len(cores))
+
+
+def cpu_reference_child(threads, steps, warmup):
+    """Runs in a FRESH process whose OpenMP environment was set by the parent before any libgomp was loaded
+    (the reference caches omp_get_max_threads() at static-init time, utils/parallel.h:51-53, and clamps every region
+    to it, :112-118): times cc->EvalMult of the unmodified reference (oracle/_ref), or the C oracle port."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle, Reference, reference_available, seeded_residues
 
-    cores = threads or len(os.sched_getaffinity(0))
     N = CFG["N"]
     if reference_available():
         ref = Reference()
-        ref.L.ref_set_threads(cores)
+        ref.L.ref_set_threads(threads)
+        used = int(ref.L.ref_get_threads())
         c = ref.ckks(N, CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
         kind = "reference"
     else:
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        used = threads
         c = Oracle().ckks(N, CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
         kind = "port"
     sizeQl = c.sizeQ
@@ -115,9 +132,47 @@ def cpu_reference_run(steps, warmup, threads=None):
             c.evalmult(sizeQl, ct1, ct2, ea, eb)
         sec = (time.perf_counter() - t0) / steps
     c.close()
-    return dict(value=1.0 / sec, unit=UNIT, cores=cores, kind=kind,
-                sample=f"{steps} EvalMult calls after {warmup} warm-up on the full workload "
-                       f"({'cc->EvalMult of the unmodified reference, OpenMP' if kind == 'reference' else 'C oracle port, OpenMP'})"), sec
+    print(json.dumps(dict(threads=used, sec_per_op=sec, kind=kind)))
+    return 0
+
+
+def cpu_reference_run(steps, warmup, budget_s=150.0):
+    """CPU arm: the reference's own EvalMult on this box's host cores, swept over thread counts
+    {1, ..., physical cores, all hardware threads} (SURVEY 8 d), every point in a fresh child process with
+    OMP_NUM_THREADS / OMP_PROC_BIND / OMP_PLACES set BEFORE the reference library (and its libgomp) is loaded --
+    torchrun's exported OMP_NUM_THREADS=1 is overridden.  value = the BEST point; the whole sweep is reported."""
+    logical, physical = host_topology()
+    cand = sorted({t for t in (1, 8, 16, 32, 64, physical, logical) if 1 <= t <= logical})
+    # most informative first, so a tight time budget still sees them: physical cores, all threads, then the rest
+    order = [physical, logical] + [t for t in cand if t not in (physical, logical)]
+    sweep, kind, t_start = {}, None, time.perf_counter()
+    for t in order:
+        if sweep and time.perf_counter() - t_start > budget_s:
+            break
+        env = dict(os.environ)
+        env.update(OMP_NUM_THREADS=str(t), OMP_PROC_BIND="close" if t <= physical else "false",
+                   OMP_PLACES="cores" if t <= physical else "threads", OMP_DYNAMIC="false")
+        env.pop("OMP_THREAD_LIMIT", None)
+        n_steps = steps if t > 1 else max(1, min(steps, 2))
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-child", str(t), "--steps", str(n_steps),
+                                  "--warmup", str(warmup)], env=env, capture_output=True, text=True, timeout=600)
+            rec = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as ex:  # one failed point does not void the arm
+            print(f"[bench] reference child with {t} threads failed: {ex}", file=sys.stderr)
+            continue
+        sweep[int(rec["threads"])] = 1.0 / rec["sec_per_op"]
+        kind = rec["kind"]
+    if not sweep:
+        raise RuntimeError("no CPU reference measurement succeeded")
+    best_t = max(sweep, key=sweep.get)
+    sec = 1.0 / sweep[best_t]
+    what = "cc->EvalMult of the unmodified reference (oracle/_ref)" if kind == "reference" else "C oracle port"
+    return dict(value=sweep[best_t], unit=UNIT, cores=best_t, kind=kind,
+                sample=f"{steps} EvalMult calls after {warmup} warm-up on the full workload, {what}; fresh process per "
+                       f"thread count with OMP_NUM_THREADS/OMP_PROC_BIND/OMP_PLACES set before load; best of the sweep",
+                sweep_mults_per_s={str(k): round(v, 4) for k, v in sorted(sweep.items())},
+                host=dict(logical_cpus=logical, physical_cores=physical)), sec
 
 
 def main():
@@ -127,6 +182,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--ref-child", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="N>1: pipeline slots (independent multiplications in flight)")
     ap.add_argument("--slots1", type=int, default=2, help="N=1: independent multiplications in flight (streams)")
@@ -138,6 +194,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if a.ref_child:
+        return cpu_reference_child(a.ref_child, max(1, a.steps), max(1, a.warmup))
     if a.impl == "reference":
         if rank != 0:
             return 0

@@ -112,11 +112,23 @@ int ofhe_scale_round_create(ofhe_ring* ring, uint32_t sizeI, const uint32_t* in_
 int ofhe_bconv_apply(ofhe_bconv* t, const uint64_t* in_d, uint64_t* out_d, void* stream);
 void ofhe_bconv_destroy(ofhe_bconv* t);
 
+/* diagnostic: how many thread-block clusters of the forward / inverse NTT kernel (one cluster = one limb of a
+ * 2^logN ring, 13 <= logN <= 16) the device holds at once: fwd_inv2[0], fwd_inv2[1]                                 */
+int ofhe_ntt_cluster_occupancy(ofhe_ctx* ctx, uint32_t logN, int* fwd_inv2);
+
 /* ---- hybrid key switching.  The ring must hold Q at indices [0,sizeQ) and P at [sizeQ, sizeQ+sizeP).
  *      Tables: CryptoParametersRNS::PrecomputeCRTTables      pke/lib/schemerns/rns-cryptoparameters.cpp:48-401
  *              CryptoParametersCKKSRNS::PrecomputeCRTTables  pke/lib/scheme/ckksrns/ckksrns-cryptoparameters.cpp:44-160 */
 int ofhe_hks_create(ofhe_ring* ring, uint32_t sizeQ, uint32_t sizeP, uint32_t numPartQ, ofhe_hks** out);
 void ofhe_hks_destroy(ofhe_hks* hks);
+/* Concurrency and capture contract of every fused entry point below (modup .. bfv_evalmult): workspace comes from a
+ * per-(context, stream) arena, so calls on DIFFERENT streams of one context / ring / hks / evk are independent and may
+ * be issued from different host threads (the reference's callers sit inside `omp parallel for`,
+ * keyswitch-hybrid.cpp:423, ckksrns-fhe.cpp:1943); calls on ONE stream are ordered by the stream.  The first call
+ * at a level on a stream allocates (level tables: once per hks; arena: once per stream) -- that is a cudaMalloc, not
+ * legal under stream capture.  ofhe_hks_reserve does both ahead of time for (sizeQl, stream): after it, every entry
+ * point at that level is asynchronous and capturable on that stream.                                                */
+int ofhe_hks_reserve(ofhe_hks* hks, uint32_t sizeQl, void* stream);
 uint32_t ofhe_hks_num_per_part(const ofhe_hks* hks); /* alpha = GetNumPerPartQ()  rns-cryptoparameters.h:401 */
 /* table read-back for parity checks against the reference getters (rns-cryptoparameters.h:314-560).
  * which: 0 PInvModq[sizeQ]  1 PModq[sizeQ]  2 PHatInvModp[sizeP]  3 PHatModq[sizeP][sizeQ]

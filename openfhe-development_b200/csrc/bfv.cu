@@ -92,7 +92,7 @@ void BfvMult::evalmult(Hks& hks, const uint64_t* ct1, const uint64_t* ct2, const
     uint64_t* c3   = scratch() + N * (2 * QR + 2 * QR + 2 * Q + 3 * QR);
     evalmult_norelin(ct1, ct2, c3, st);
     launch_ntt_fwd(r, c3, c3, map_q3, st);  // RelinearizeCore: cv[sel].SetFormat(EVALUATION), cv[0/1].SetFormat (:915,926)
-    uint64_t* ws = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * hks.workspace_words(sizeQ)));
+    uint64_t* ws = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * hks.workspace_words(sizeQ), st));
     hks.keyswitch_core(sizeQ, c3 + 2 * Q * N, evk, out, c3, ws, st);  // ab = KeySwitchCore(c2); c0 += ab0; c1 += ab1
 }
 

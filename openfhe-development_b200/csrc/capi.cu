@@ -510,11 +510,27 @@ void ofhe_evk_destroy(ofhe_evk* evk) {
     }
 }
 
+int ofhe_ntt_cluster_occupancy(ofhe_ctx* ctx, uint32_t logN, int* fwd_inv2) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        ntt_cluster_occupancy(logN, fwd_inv2);
+    });
+}
+int ofhe_hks_reserve(ofhe_hks* hks, uint32_t sizeQl, void* stream) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        h.level(sizeQl);
+        if (sizeQl >= 2)
+            h.level(sizeQl - 1);  // rescale reads the next level's limb map
+        h.ring->ctx->get_scratch(sizeof(uint64_t) * h.max_workspace_words(sizeQl), S(stream));
+    });
+}
 int ofhe_hks_modup(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* c_d, uint64_t* digits_d, void* stream) {
     return guard([&] {
         Hks& h = *hks->h;
         use(h.ring);
-        uint64_t* tmp = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl)));
+        uint64_t* tmp = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl), S(stream)));
         h.modup(sizeQl, c_d, digits_d, tmp, S(stream));
     });
 }
@@ -533,7 +549,7 @@ int ofhe_hks_approx_mod_down(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* in_
         use(h.ring);
         OFHE_REQUIRE(n_polys == 1 || n_polys == 2, "n_polys must be 1 or 2");
         const size_t N = h.ring->N, sizeQlP = sizeQl + h.sizeP;
-        uint64_t* ws = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl)));
+        uint64_t* ws = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl), S(stream)));
         if (n_polys == 2) {
             h.mod_down2(sizeQl, in_d, out_d, nullptr, ws, ws + 2 * (size_t)h.sizeP * N, S(stream));
         }
@@ -556,7 +572,7 @@ int ofhe_hks_keyswitch_core(ofhe_hks* hks, uint32_t sizeQl, const uint64_t* c_d,
     return guard([&] {
         Hks& h = *hks->h;
         use(h.ring);
-        uint64_t* ws = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl)));
+        uint64_t* ws = static_cast<uint64_t*>(h.ring->ctx->get_scratch(sizeof(uint64_t) * h.workspace_words(sizeQl), S(stream)));
         h.keyswitch_core(sizeQl, c_d, *evk->k, out01_d, nullptr, ws, S(stream));
     });
 }

@@ -10,23 +10,31 @@
 
 namespace ofhe {
 
-void* Context::get_scratch(size_t bytes) {
+void* Context::get_scratch(size_t bytes, cudaStream_t st) {
     std::lock_guard<std::mutex> g(mu);
-    if (bytes > scratch_bytes) {
-        // the old block may still be in use by queued kernels: free is stream-ordered after a device sync
-        if (scratch) {
-            OFHE_CUDA(cudaDeviceSynchronize());
-            OFHE_CUDA(cudaFree(scratch));
-            scratch = nullptr;
-        }
-        OFHE_CUDA(cudaMalloc(&scratch, bytes));
-        scratch_bytes = bytes;
+    Arena& a = arenas[st];
+    if (bytes > a.bytes) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (st != nullptr)
+            OFHE_CUDA(cudaStreamIsCapturing(st, &cs));
+        OFHE_REQUIRE(cs == cudaStreamCaptureStatusNone,
+                     "workspace of this stream must grow during stream capture: call ofhe_hks_reserve (or run the "
+                     "operation once eagerly) on the stream before capturing");
+        if (a.p)
+            retired.push_back(a.p);  // queued kernels / captured graphs may still reference it
+        a.p = nullptr;
+        a.bytes = 0;
+        OFHE_CUDA(cudaMalloc(&a.p, bytes));
+        a.bytes = bytes;
     }
-    return scratch;
+    return a.p;
 }
 Context::~Context() {
-    if (scratch)
-        cudaFree(scratch);
+    for (auto& kv : arenas)
+        if (kv.second.p)
+            cudaFree(kv.second.p);
+    for (void* p : retired)
+        cudaFree(p);
 }
 
 Ring::~Ring() {

@@ -210,6 +210,11 @@ size_t Hks::workspace_words(uint32_t sizeQl) const {
     return N * ((size_t)sizeQl + (size_t)dnum * sizeQlP + 2 * sizeQlP + 2 * sizeP + 2 * (size_t)sizeQl + sizeQl);
 }
 
+size_t Hks::max_workspace_words(uint32_t sizeQl) const {
+    const size_t N = ring->N, P = (size_t)sizeQl * N, E = (size_t)(sizeQl + sizeP) * N;
+    return std::max(workspace_words(sizeQl) + 2 * P, 2 * E + 2 * sizeP * N + 4 * P);
+}
+
 void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st) {
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
@@ -287,7 +292,7 @@ void Hks::evalmult(uint32_t sizeQl, const uint64_t* ct1, const uint64_t* ct2, co
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, P = (size_t)sizeQl * N;
-    uint64_t* ws = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * workspace_words(sizeQl)));
+    uint64_t* ws = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * workspace_words(sizeQl), st));
     uint64_t* c2 = ws + (workspace_words(sizeQl) - P);
     // tensor product: out = (c0, c1), c2 to scratch                                     (base-leveledshe.cpp:620-624)
     launch_tensor(r, ct1, ct1 + P, ct2, ct2 + P, out, out + P, c2, lv.map_Ql, st);
@@ -302,7 +307,7 @@ void Hks::rescale(uint32_t sizeQl, const uint64_t* in, uint64_t* out, uint32_t n
     const Ring& r  = *ring;
     const size_t N = r.N;
     const uint32_t l = sizeQl - 1;
-    uint64_t* ws   = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * N * (1 + (size_t)l)));
+    uint64_t* ws   = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * N * (1 + (size_t)l), st));
     uint64_t* z    = ws;
     uint64_t* t    = ws + N;
     uint32_t last  = l;
@@ -322,7 +327,7 @@ void Hks::rotate(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const EvalKey&
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, P = (size_t)sizeQl * N;
-    uint64_t* ws  = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * (workspace_words(sizeQl) + 2 * P)));
+    uint64_t* ws  = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * (workspace_words(sizeQl) + 2 * P), st));
     uint64_t* tmp = ws + workspace_words(sizeQl);
     // KeySwitchInPlace on a 2-element ciphertext: (c0 + ab0, ab1), ab = KeySwitchCore(c1)   (keyswitch-hybrid.cpp:199-214)
     // the addend for the second polynomial is absent, so run the two ModDown tails separately via a zeroed addend
@@ -342,7 +347,7 @@ void Hks::fast_rotation(uint32_t sizeQl, uint32_t k, const uint64_t* ct, const u
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, P = (size_t)sizeQl * N, E = (size_t)(sizeQl + sizeP) * N;
-    uint64_t* ws    = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * (2 * E + 2 * sizeP * N + 4 * P)));
+    uint64_t* ws    = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * (2 * E + 2 * sizeP * N + 4 * P), st));
     uint64_t* e01   = ws;
     uint64_t* p_tmp = e01 + 2 * E;
     uint64_t* conv  = p_tmp + 2 * (size_t)sizeP * N;
@@ -361,7 +366,7 @@ void Hks::fast_rotation_ext(uint32_t sizeQl, uint32_t k, bool add_first, const u
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, E = (size_t)(sizeQl + sizeP) * N;
-    uint64_t* e01  = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * 2 * E));
+    uint64_t* e01  = static_cast<uint64_t*>(r.ctx->get_scratch(sizeof(uint64_t) * 2 * E, st));
     inner_product(sizeQl, lv.n_digits, digits, evk, e01, st);
     if (add_first)  // :561-570
         launch_mul_scalars_add(r, e01, ct, pmodq_sv, e01, lv.map_Ql, st);

@@ -46,6 +46,7 @@ struct Hks {
     ~Hks();
     Level& level(uint32_t sizeQl);
     size_t workspace_words(uint32_t sizeQl) const;
+    size_t max_workspace_words(uint32_t sizeQl) const;  // the largest arena any entry point asks for at this level
 
     // c [sizeQl][N] EVALUATION -> digits [n_digits][sizeQl+sizeP][N] EVALUATION; coeff_tmp [sizeQl][N] scratch
     void modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st);

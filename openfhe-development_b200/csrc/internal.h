@@ -64,11 +64,20 @@ struct Error : std::runtime_error {
 struct Context {
     int device = 0;
     int sm_count = 0;
-    // scratch arena for the fused pipelines (grown on demand, never shrunk)
-    void* scratch = nullptr;
-    size_t scratch_bytes = 0;
+    // Scratch arenas for the fused pipelines, ONE PER STREAM: calls issued on different streams of the same
+    // context (the reference's callers sit inside their own `omp parallel for`, keyswitch-hybrid.cpp:423,
+    // ckksrns-fhe.cpp:1943) never share workspace, calls on one stream are ordered by the stream.  An arena only
+    // grows; an outgrown block is retired (kept until the context dies) so that kernels already queued on it and
+    // CUDA graphs that captured its address stay valid.  Growing is a cudaMalloc: it is refused while the stream
+    // is being captured -- pre-size with ofhe_hks_reserve() (or one eager call) before capturing.
+    struct Arena {
+        void* p = nullptr;
+        size_t bytes = 0;
+    };
+    std::map<cudaStream_t, Arena> arenas;
+    std::vector<void*> retired;
     std::mutex mu;
-    void* get_scratch(size_t bytes);
+    void* get_scratch(size_t bytes, cudaStream_t st);
     ~Context();
 };
 
@@ -110,6 +119,7 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
 // folded in, see make_inv_fold(); nullptr = plain inverse transform.
 void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
                     const PosMap* out_pos = nullptr, const uint64_t* fold = nullptr, const PeerOut* peers = nullptr);
+void ntt_cluster_occupancy(uint32_t logN, int out[2]);  // diagnostic, see ntt.cu
 // host helper: the four folded constants of limb `mod_idx` for extra scalar s
 void make_inv_fold(const Ring& r, uint32_t mod_idx, uint64_t s, uint64_t out4[4]);
 

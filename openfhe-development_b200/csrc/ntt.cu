@@ -6,157 +6,316 @@
 // Same contract: forward = natural order in, bit-reversed order out; inverse = the opposite; canonical
 // residues in [0,q) on exit; twiddle tables T[brev(i)] = psi^i with Shoup constants.
 //
-// B200 decomposition (not the reference's stage-by-stage loop):
-//   forward :  [strided kernel: first logN-12 stages, 2^(logN-12) points per thread, no shared memory]
-//              [tile kernel   : last 12 stages on contiguous 4096-point tiles (32 KiB of shared memory),
-//                               three radix-16 register rounds with two swizzled smem exchanges]
-//   inverse :  the mirror image (tile kernel first, strided kernel last with N^-1 folded in).
-// Butterflies are Harvey-lazy: forward values live in [0,4q), inverse values in [0,2q); one final
-// conditional subtraction makes the output canonical, hence bit-identical to the reference.
-// The intermediate between the two kernels stays L2-resident for slabs that fit the 126 MB L2.
-#include "internal.h"
+// B200 decomposition (not the reference's stage-by-stage loop), N = 2^(12+A), A = 0..4:
+//   ONE kernel, ONE pass over HBM.  A limb is transformed by a thread-block CLUSTER of 2^A CTAs; CTA c owns
+//   the contiguous 4096-point tile c (32 KiB of shared memory), 256 threads x 16 points.
+//   forward : phase A -- the A stages whose butterfly span is >= 4096: every thread loads 16 points with stride
+//                        4096 straight from HBM (a warp reads 256 contiguous bytes per point), runs a radix-2^A
+//                        register round and scatters result k into tile k of CTA k through DISTRIBUTED SHARED
+//                        MEMORY (st.shared::cluster, 256 contiguous bytes per warp and destination);
+//             cluster barrier;
+//             phase B -- the last 12 stages on the CTA's own tile: three radix-16 register rounds with two
+//                        shared-memory exchanges (the second XOR-swizzled), 128-bit stores of canonical residues.
+//   inverse : the mirror image (phase B first, DSMEM scatter, cluster barrier, strided radix-2^A round with
+//             N^-1 -- and optionally one more per-limb scalar -- folded into the last stage, optionally storing the
+//             finished rows into several destination buffers at once: NVLink peer pushes of shard.cu).
+//   N = 2^17 (a limb does not fit 16 x 32 KiB) keeps the two-kernel split [strided | tile] through L2;
+//   N < 4096 (the reference's unit-test sizes) runs one CTA per limb in shared memory.
+// Butterflies: see ntt_core.cuh (truncated Shoup quotient, compile-time lazy range schedule).
+#include <algorithm>
+#include <cstdlib>
+
+#include "ntt_core.cuh"
 
 namespace ofhe {
 
 namespace {
+using namespace nttc;
 // NOTE: `in` and `out` may be the same slab (in-place transforms), so data pointers carry no __restrict__.
 
-__device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
-    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
-    return Twiddle{v.x, v.y};
+constexpr int kTile = 4096;
+__device__ __forceinline__ uint32_t swz(uint32_t c) {
+    return c ^ ((c >> 4) & 15u);
 }
 
-// Lazy-range discipline (Harvey).  On sm_100 the integer multiplier (IMAD.WIDE: 4 issue cycles per warp on the
-// fmaheavy pipe, 2 for a 32-bit IMAD) is the bottleneck of a 60-bit butterfly: a Shoup product costs 6 IMAD.WIDE +
-// 4 IMAD = 32 cycles, while the ALU pipe (IADD3 / ISETP / SEL, 2 cycles each) has ~16 instruction slots to spare in
-// that time.  So range control is done with conditional subtractions on the ALU pipe (not with multiply-based
-// reductions), one per butterfly:  forward values live in [0,4q), inverse values in [0,2q).
-struct Mod {
-    uint64_t q, nq, twoq, one_s;  // nq = 2^64 - q
-};
-__device__ __forceinline__ Mod make_mod(const ModConst& mc) {
-    return Mod{mc.q, 0 - mc.q, 2 * mc.q, mc.one_s};
-}
-// Cooley-Tukey butterfly, inputs/outputs in [0,4q)
-__device__ __forceinline__ void ct_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, const Mod& m) {
-    const uint64_t x = X >= m.twoq ? X - m.twoq : X;        // [0,2q)
-    const uint64_t v = shoup_lazy_n(Y, t.w, t.ws, m.nq);   // [0,2q)
-    X                = x + v;
-    Y                = x - v + m.twoq;
-}
-// Gentleman-Sande butterfly, inputs/outputs in [0,2q)
-__device__ __forceinline__ void gs_bfly(uint64_t& X, uint64_t& Y, const Twiddle& t, const Mod& m) {
-    const uint64_t s = X + Y;
-    const uint64_t d = X - Y + m.twoq;
-    X                = s >= m.twoq ? s - m.twoq : s;
-    Y                = shoup_lazy_n(d, t.w, t.ws, m.nq);
+// finished rows -> one or several destination slabs (PeerOut); constant indices keep the pointer array in the
+// kernel parameter bank (a run-time index would force a local-memory copy)
+template <typename F>
+__device__ __forceinline__ void for_each_dest(uint64_t* out, const PeerOut& po, F&& f) {
+    if (po.n == 0) {
+        f(out);
+        return;
+    }
+#pragma unroll
+    for (uint32_t d = 0; d < kMaxPeers; ++d)
+        if (d < po.n)
+            f(po.base[d]);
 }
 
-// One stage (local depth D of R) on 2^R register-resident points; all indices are compile-time constants so the
-// point array stays in registers.  x[k]: local index k, MSB = the round's first stage bit.
-// tw_base = 2^s0 + u (s0 = the round's first global stage, u = the s0 index bits above this group).
-template <int R, int D>
-__device__ __forceinline__ void ct_stage(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         const Mod& m) {
-    constexpr int half = 1 << (R - 1 - D);
+// ---- phase B of the forward transform: stages S0 .. S0+11 on the tile held in sm (linear layout on entry) ----
+// FROM_GLOBAL: S0 == 0 (N = 4096), round A reads the canonical input straight from `in`.
+template <int LOGN>
+__device__ __forceinline__ void fwd_tile_rounds(uint64_t* sm, uint64_t (&x)[16], const Twiddle* tw, uint32_t tile,
+                                                const Mod& m, uint32_t t) {
+    constexpr int S0 = LOGN - 12;
+    const uint32_t bh = t >> 4, bl = t & 15u;
+    // ---- round A: tile bits 11..8, thread t holds c = t + 256k (already in x)
+    prefetch_round(tw, ((1u << S0) + tile) * 16u + bh);
+    ct_round<LOGN, S0, 4>(x, tw, (1u << S0) + tile, m);
 #pragma unroll
-    for (int g = 0; g < (1 << D); ++g) {
-        const Twiddle t = ld_tw(tw + ((tw_base << D) + g));
+    for (int k = 0; k < 16; ++k)
+        sm[t + 256 * k] = x[k];
+    __syncthreads();
+    // ---- round B: tile bits 7..4, c = (t>>4)*256 + (t&15) + 16k
+    prefetch_round(tw, ((1u << S0) + tile) * 256u + t);
 #pragma unroll
-        for (int l = 0; l < half; ++l)
-            ct_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, m);
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[bh * 256 + bl + 16 * k];
+    ct_round<LOGN, S0 + 4, 4>(x, tw, ((1u << S0) + tile) * 16u + bh, m);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[swz(bh * 256 + bl + 16 * k)] = x[k];
+    __syncthreads();
+    // ---- round C: tile bits 3..0, c = 16t + k (128 contiguous bytes per thread)
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[swz(16 * t + k)];
+#if defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 1
+    ct_round<LOGN, S0 + 8, 4>(x, tw, ((1u << S0) + tile) * 256u + (t >> 5), m);  // TIMING EXPERIMENT ONLY (wrong results)
+#elif defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 2
+    ct_round<LOGN, S0 + 8, 4>(x, tw, 1u, m);  // TIMING EXPERIMENT ONLY (wrong results)
+#else
+    ct_round<LOGN, S0 + 8, 4>(x, tw, ((1u << S0) + tile) * 256u + t, m);
+#endif
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = canon8(x[k], m);
+}
+// ---- phase B of the inverse transform: stages LOGN-1 .. LOGN-12 (mirror order); on exit thread t holds tile
+// offsets t + 256k.  LAST: N = 4096, round A contains the folded final stage.
+template <bool LAST>
+__device__ __forceinline__ void inv_tile_rounds(uint64_t* sm, uint64_t (&x)[16], const Twiddle* tw, uint32_t tbase,
+                                                const LastConst& lc, const Mod& m, uint32_t t) {
+    // tbase = 2^S0 + tile
+    const uint32_t bh = t >> 4, bl = t & 15u;
+    prefetch_round(tw, tbase * 16u + bh);
+    gs_round<4, false>(x, tw, tbase * 256u + t, lc, m);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[swz(16 * t + k)] = x[k];
+    __syncthreads();
+    prefetch_round(tw, tbase);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[swz(bh * 256 + bl + 16 * k)];
+    gs_round<4, false>(x, tw, tbase * 16u + bh, lc, m);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        sm[bh * 256 + bl + 16 * k] = x[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = sm[t + 256 * k];
+    gs_round<4, LAST>(x, tw, tbase, lc, m);
+}
+
+// phase A register rounds: G independent columns of 2^A strided points each, x[g * 2^A + k]
+template <int LOGN, int A, int G, int g = 0>
+__device__ __forceinline__ void fwd_columns(uint64_t* x, const Twiddle* tw, const Mod& m) {
+    if constexpr (g < G) {
+        ct_round<LOGN, 0, A, g * (1 << A)>(x, tw, 1u, m);
+        fwd_columns<LOGN, A, G, g + 1>(x, tw, m);
     }
 }
-template <int R, int D>
-__device__ __forceinline__ void gs_stage(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         const Mod& m) {
-    constexpr int half = 1 << (R - 1 - D);
-#pragma unroll
-    for (int g = 0; g < (1 << D); ++g) {
-        const Twiddle t = ld_tw(tw + ((tw_base << D) + g));
-#pragma unroll
-        for (int l = 0; l < half; ++l)
-            gs_bfly(x[(g << (R - D)) + l], x[(g << (R - D)) + l + half], t, m);
+template <int A, int G, int g = 0>
+__device__ __forceinline__ void inv_columns(uint64_t* x, const Twiddle* tw, const LastConst& lc, const Mod& m) {
+    if constexpr (g < G) {
+        gs_round<A, true, g * (1 << A)>(x, tw, 1u, lc, m);
+        inv_columns<A, G, g + 1>(x, tw, lc, m);
     }
-}
-// The four constants (nInv, Shoup(nInv), Tinv[1]*nInv, Shoup(..)) may carry an extra per-limb scalar folded in by
-// the caller (e.g. QHatInvModq ahead of a base conversion): INTT(x) * s costs nothing extra.
-struct LastConst {
-    uint64_t a, as, b, bs;
-};
-__device__ __forceinline__ LastConst last_const(const ModConst& mc, const uint64_t* __restrict__ fold, uint32_t limb) {
-    if (fold)
-        return LastConst{fold[4 * limb], fold[4 * limb + 1], fold[4 * limb + 2], fold[4 * limb + 3]};
-    return LastConst{mc.nInv, mc.nInvS, mc.w1nInv, mc.w1nInvS};
-}
-template <int R>
-__device__ __forceinline__ void gs_last_stage(uint64_t (&x)[1 << R], const LastConst& lc, const Mod& m) {
-    constexpr int half = 1 << (R - 1);
-#pragma unroll
-    for (int l = 0; l < half; ++l) {
-        const uint64_t s = x[l] + x[l + half];
-        const uint64_t e = x[l] - x[l + half] + m.twoq;
-        x[l]             = shoup(s, lc.a, lc.as, m.q);
-        x[l + half]      = shoup(e, lc.b, lc.bs, m.q);
-    }
-}
-
-// R consecutive CT stages, [0,4q) -> [0,4q)
-template <int R>
-__device__ __forceinline__ void ct_round(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         const Mod& m) {
-    ct_stage<R, 0>(x, tw, tw_base, m);
-    if constexpr (R > 1) ct_stage<R, 1>(x, tw, tw_base, m);
-    if constexpr (R > 2) ct_stage<R, 2>(x, tw, tw_base, m);
-    if constexpr (R > 3) ct_stage<R, 3>(x, tw, tw_base, m);
-    if constexpr (R > 4) ct_stage<R, 4>(x, tw, tw_base, m);
-}
-// R consecutive GS stages (mirror order), [0,2q) -> [0,2q).  If LAST, depth 0 is the transform's final stage
-// (canonical outputs).
-template <int R, bool LAST>
-__device__ __forceinline__ void gs_round(uint64_t (&x)[1 << R], const Twiddle* __restrict__ tw, uint32_t tw_base,
-                                         const LastConst& lc, const Mod& m) {
-    if constexpr (R > 4) gs_stage<R, 4>(x, tw, tw_base, m);
-    if constexpr (R > 3) gs_stage<R, 3>(x, tw, tw_base, m);
-    if constexpr (R > 2) gs_stage<R, 2>(x, tw, tw_base, m);
-    if constexpr (R > 1) gs_stage<R, 1>(x, tw, tw_base, m);
-    if constexpr (LAST)
-        gs_last_stage<R>(x, lc, m);
-    else
-        gs_stage<R, 0>(x, tw, tw_base, m);
-}
-
-__device__ __forceinline__ uint64_t canon(uint64_t v, const Mod& m) {  // [0,4q) -> [0,q)
-    v = v >= m.twoq ? v - m.twoq : v;
-    return v >= m.q ? v - m.q : v;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Strided kernels: the A = logN - 12 stages whose butterfly span is >= 4096.  One thread owns the 2^A
-// points {c + k * N/2^A}; a warp's loads are 256 contiguous bytes per k.  Twiddles T[1 .. 2^A) are
-// warp-uniform.  No shared memory.
+// Cluster kernels.  grid = (2^A, limbs), cluster = (2^A, 1, 1), 256 threads.  CL = 2^A tiles, G = 16 / CL
+// columns of CL strided points per thread in phase A.
+#ifndef OFHE_NTT_MINB
+#define OFHE_NTT_MINB 3  // resident CTAs per SM the kernels are compiled for (register cap 65536 / (256 * MINB))
+#endif
 template <int A>
-__global__ void __launch_bounds__(256) ntt_fwd_strided(RingDev r, const uint64_t* in,
-                                                        uint64_t* out, LimbMap lm, PosMap op) {
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_cluster(RingDev r, const uint64_t* in, uint64_t* out,
+                                                                        LimbMap lm, PosMap op) {
+    constexpr int LOGN = 12 + A, CL = 1 << A, G = 16 / CL;
+    __shared__ __align__(16) uint64_t sm[kTile];
+    const uint32_t limb = blockIdx.y, t = threadIdx.x;
+    const uint32_t c    = A ? cluster_ctarank() : 0u;
+    const uint32_t mi   = lm.idx[limb];
+    const Mod m         = make_mod(r.mc[mi]);
+    const Twiddle* tw   = r.tw_fwd + (size_t)mi * r.N;
+    const uint64_t* src = in + (size_t)lm.pos[limb] * r.N;
+    uint64_t* dst       = out + (size_t)op.pos[limb] * r.N + (size_t)c * kTile;
+    uint64_t x[16];
+    prefetch_round(tw, (1u << A) + c);
+    if constexpr (A == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            x[k] = __ldcs(src + t + 256 * k);
+    }
+    else {
+        cluster_arrive_relaxed();  // every CTA of the cluster is running before anyone touches its shared memory
+        // ---- phase A: columns j = (c*G + g)*256 + t, points j + 4096k
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int k = 0; k < CL; ++k)
+                x[g * CL + k] = __ldcs(src + (c * G + g) * 256 + t + (size_t)kTile * k);
+        fwd_columns<LOGN, A, G>(x, tw, m);
+        // ---- scatter: point k of column j belongs to tile k, offset j
+        const uint32_t sm0 = smem_u32(sm);
+        cluster_wait();
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+            const uint32_t remote = mapa(sm0, (uint32_t)k);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                st_cluster(remote + 8u * ((c * G + g) * 256 + t), x[g * CL + k]);
+        }
+        cluster_arrive();
+        cluster_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            x[k] = sm[t + 256 * k];
+    }
+    fwd_tile_rounds<LOGN>(sm, x, tw, c, m, t);
+    ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst + 16 * t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        __stcs(d2 + k, make_ulonglong2(x[2 * k], x[2 * k + 1]));
+}
+
+template <int A>
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_cluster(RingDev r, const uint64_t* in, uint64_t* out,
+                                                                        LimbMap lm, PosMap op,
+                                                                        const uint64_t* __restrict__ fold, PeerOut po) {
+    constexpr int CL = 1 << A, G = 16 / CL;
+    extern __shared__ __align__(16) uint64_t dsm[];  // [tile 4096][receive 4096 if A > 0]
+    uint64_t* sm   = dsm;
+    uint64_t* rbuf = dsm + kTile;
+    const uint32_t limb = blockIdx.y, t = threadIdx.x;
+    const uint32_t c    = A ? cluster_ctarank() : 0u;
+    const uint32_t mi   = lm.idx[limb];
+    const ModConst mc   = r.mc[mi];
+    const Mod m         = make_mod(mc);
+    const Twiddle* tw   = r.tw_inv + (size_t)mi * r.N;
+    const LastConst lc  = last_const(mc, fold, limb);
+    const size_t obase  = (size_t)op.pos[limb] * r.N;
+    if constexpr (A > 0)
+        cluster_arrive_relaxed();
+    prefetch_round(tw, ((1u << A) + c) * 256u + t);
+    uint64_t x[16];
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(in + (size_t)lm.pos[limb] * r.N + (size_t)c * kTile + 16 * t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const ulonglong2 v = __ldcs(src + k);
+        x[2 * k]           = v.x;
+        x[2 * k + 1]       = v.y;
+    }
+    inv_tile_rounds<A == 0>(sm, x, tw, (1u << A) + c, lc, m, t);
+    if constexpr (A == 0) {
+        for_each_dest(out, po, [&](uint64_t* o) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                o[obase + t + 256 * k] = x[k];
+        });
+    }
+    else {
+        // thread t holds tile offsets t + 256k of tile c: offset 256k + t is column (k % G)*256 + t of CTA k / G
+        const uint32_t r0 = smem_u32(rbuf);
+        cluster_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            st_cluster(mapa(r0, (uint32_t)(k / G)) + 8u * (((k % G) * CL + c) * 256 + t), x[k]);
+        cluster_arrive();
+        cluster_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            x[i] = rbuf[i * 256 + t];
+        inv_columns<A, G>(x, tw, lc, m);
+        for_each_dest(out, po, [&](uint64_t* o) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int k = 0; k < CL; ++k)
+                    __stcs(o + obase + (c * G + g) * 256 + t + (size_t)kTile * k, x[g * CL + k]);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split kernels (N = 2^17 only): the A = 5 strided stages as a register round straight from/to HBM, then the
+// tile kernel; the lazy intermediate ([0,16q) forward, [0,4q) inverse) stays in L2 for slabs that fit it.
+template <int A>
+__global__ void __launch_bounds__(256) ntt_fwd_strided(RingDev r, const uint64_t* in, uint64_t* out, LimbMap lm, PosMap op) {
     const uint32_t limb   = blockIdx.y;
     const uint32_t mi     = lm.idx[limb];
     const uint32_t stride = r.N >> A;
     const uint32_t c      = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= stride)
-        return;
-    const Mod m = make_mod(r.mc[mi]);
-    const uint64_t* src = in + (size_t)lm.pos[limb] * r.N + c;
-    uint64_t* dst       = out + (size_t)op.pos[limb] * r.N + c;
+    const Mod m           = make_mod(r.mc[mi]);
+    const uint64_t* src   = in + (size_t)lm.pos[limb] * r.N + c;
+    uint64_t* dst         = out + (size_t)op.pos[limb] * r.N + c;
     uint64_t x[1 << A];
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
         x[k] = src[(size_t)k * stride];
-    ct_round<A>(x, r.tw_fwd + (size_t)mi * r.N, 1u, m);
+    ct_round<12 + A, 0, A>(x, r.tw_fwd + (size_t)mi * r.N, 1u, m);
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
-        dst[(size_t)k * stride] = x[k];  // lazy [0,4q): the tile kernel canonicalises
+        dst[(size_t)k * stride] = x[k];
 }
-
+template <int A>
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_tile(RingDev r, uint64_t* data, LimbMap lm) {
+    __shared__ __align__(16) uint64_t sm[kTile];
+    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+    const uint32_t mi   = lm.idx[limb];
+    const Mod m         = make_mod(r.mc[mi]);
+    uint64_t* p         = data + (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
+    const Twiddle* tw   = r.tw_fwd + (size_t)mi * r.N;
+    uint64_t x[16];
+    prefetch_round(tw, (1u << A) + tile);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = p[t + 256 * k];
+    fwd_tile_rounds<12 + A>(sm, x, tw, tile, m, t);
+    ulonglong2* d2 = reinterpret_cast<ulonglong2*>(p + 16 * t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        d2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
+}
+template <int A>
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_tile(RingDev r, const uint64_t* in, uint64_t* out,
+                                                                     LimbMap lm, PosMap op) {
+    __shared__ __align__(16) uint64_t sm[kTile];
+    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+    const uint32_t mi   = lm.idx[limb];
+    const ModConst mc   = r.mc[mi];
+    const Mod m         = make_mod(mc);
+    const Twiddle* tw   = r.tw_inv + (size_t)mi * r.N;
+    uint64_t x[16];
+    prefetch_round(tw, ((1u << A) + tile) * 256u + t);
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(in + (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile + 16 * t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const ulonglong2 v = src[k];
+        x[2 * k]           = v.x;
+        x[2 * k + 1]       = v.y;
+    }
+    inv_tile_rounds<false>(sm, x, tw, (1u << A) + tile, LastConst{}, m, t);
+    uint64_t* o = out + (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        o[t + 256 * k] = x[k];
+}
 template <int A>
 __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data, LimbMap lm,
                                                         const uint64_t* __restrict__ fold, PeerOut po) {
@@ -164,158 +323,31 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data
     const uint32_t mi     = lm.idx[limb];
     const uint32_t stride = r.N >> A;
     const uint32_t c      = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= stride)
-        return;
-    const ModConst mc = r.mc[mi];
-    const Mod m       = make_mod(mc);
-    uint64_t* p = data + (size_t)lm.pos[limb] * r.N + c;
+    const ModConst mc     = r.mc[mi];
+    const Mod m           = make_mod(mc);
+    const size_t off      = (size_t)lm.pos[limb] * r.N + c;
     uint64_t x[1 << A];
 #pragma unroll
     for (int k = 0; k < (1 << A); ++k)
-        x[k] = p[(size_t)k * stride];
+        x[k] = data[off + (size_t)k * stride];
     gs_round<A, true>(x, r.tw_inv + (size_t)mi * r.N, 1u, last_const(mc, fold, limb), m);
-    // every point passed through the folded last stage => already canonical
-    if (po.n == 0) {
+    for_each_dest(data, po, [&](uint64_t* o) {
 #pragma unroll
         for (int k = 0; k < (1 << A); ++k)
-            p[(size_t)k * stride] = x[k];
-    }
-    else {  // push the finished rows into every destination buffer (local one included)
-        const size_t off = (size_t)lm.pos[limb] * r.N + c;
-        for (uint32_t d = 0; d < po.n; ++d) {
-            uint64_t* q = po.base[d] + off;
-#pragma unroll
-            for (int k = 0; k < (1 << A); ++k)
-                q[(size_t)k * stride] = x[k];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Tile kernels: 12 stages on a contiguous tile of 4096 points, 256 threads x 16 points.
-//   round A: tile bits 11..8   thread t holds c = t + 256k              (coalesced global access)
-//   round B: tile bits  7..4   thread t holds c = (t>>4)*256 + (t&15) + 16k
-//   round C: tile bits  3..0   thread t holds c = 16t + k               (128 contiguous bytes / thread)
-// Exchange A<->B is conflict-free in linear layout; B<->C uses the swizzle c ^ ((c>>4)&15).
-constexpr int kTile = 4096;
-#ifndef OFHE_TILE_MINB
-#define OFHE_TILE_MINB 3  // resident CTAs per SM the tile kernels are compiled for (register cap 65536/(256*MINB))
-#endif
-__device__ __forceinline__ uint32_t swz(uint32_t c) {
-    return c ^ ((c >> 4) & 15u);
-}
-
-template <bool SINGLE>  // SINGLE: logN == 12, input is canonical and no strided kernel ran before
-__global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_fwd_tile(RingDev r, const uint64_t* in,
-                                                     uint64_t* out, LimbMap lm, PosMap op) {
-    __shared__ uint64_t sm[kTile];
-    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
-    const uint32_t mi = lm.idx[limb];
-    const Mod m         = make_mod(r.mc[mi]);
-    const Twiddle* tw   = r.tw_fwd + (size_t)mi * r.N;
-    const uint32_t s0   = r.logN - 12;  // first stage handled here
-    const size_t base   = (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
-    const size_t obase  = (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
-    uint64_t x[16];
-    // ---- round A
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        x[k] = in[base + t + 256 * k];
-    ct_round<4>(x, tw, (1u << s0) + tile, m);
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        sm[t + 256 * k] = x[k];
-    __syncthreads();
-    // ---- round B
-    const uint32_t bh = t >> 4, bl = t & 15u;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        x[k] = sm[bh * 256 + bl + 16 * k];
-    ct_round<4>(x, tw, ((1u << s0) + tile) * 16u + bh, m);
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        sm[swz(bh * 256 + bl + 16 * k)] = x[k];
-    __syncthreads();
-    // ---- round C
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        x[k] = sm[swz(16 * t + k)];
-    ct_round<4>(x, tw, ((1u << s0) + tile) * 256u + t, m);
-    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + obase + 16 * t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        dst[k] = make_ulonglong2(canon(x[2 * k], m), canon(x[2 * k + 1], m));
-}
-
-template <bool SINGLE>  // SINGLE: logN == 12, the folded last stage happens in round A
-__global__ void __launch_bounds__(256, OFHE_TILE_MINB) ntt_inv_tile(RingDev r, const uint64_t* in,
-                                                     uint64_t* out, LimbMap lm, PosMap op,
-                                                     const uint64_t* __restrict__ fold, PeerOut po) {
-    __shared__ uint64_t sm[kTile];
-    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
-    const uint32_t mi = lm.idx[limb];
-    const ModConst mc = r.mc[mi];
-    const Mod m       = make_mod(mc);
-    const Twiddle* tw = r.tw_inv + (size_t)mi * r.N;
-    const uint32_t s0 = r.logN - 12;
-    const size_t base = (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
-    const size_t obase = (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
-    uint64_t x[16];
-    // ---- round C (stages logN-1 .. logN-4)
-    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(in + base + 16 * t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        ulonglong2 v = src[k];
-        x[2 * k]     = v.x;
-        x[2 * k + 1] = v.y;
-    }
-    const LastConst lc = last_const(mc, SINGLE ? fold : nullptr, limb);
-    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 256u + t, lc, m);  // canonical input
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        sm[swz(16 * t + k)] = x[k];
-    __syncthreads();
-    // ---- round B
-    const uint32_t bh = t >> 4, bl = t & 15u;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        x[k] = sm[swz(bh * 256 + bl + 16 * k)];
-    gs_round<4, false>(x, tw, ((1u << s0) + tile) * 16u + bh, lc, m);
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        sm[bh * 256 + bl + 16 * k] = x[k];
-    __syncthreads();
-    // ---- round A
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        x[k] = sm[t + 256 * k];
-    gs_round<4, SINGLE>(x, tw, (1u << s0) + tile, lc, m);
-    if (!SINGLE || po.n == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            out[obase + t + 256 * k] = x[k];  // SINGLE: canonical; else lazy [0,2q), finished by the strided kernel
-    }
-    else {
-        for (uint32_t d = 0; d < po.n; ++d)
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                po.base[d][obase + t + 256 * k] = x[k];
-    }
+            o[off + (size_t)k * stride] = x[k];
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
 // Small rings (N < 4096: the reference's unit-test sizes): one CTA per limb, whole limb in shared memory,
-// one stage per barrier.  Not a performance path.
+// one stage per barrier.  Not a performance path.  Forward points stay below 8q (X reduced below 4q every stage).
 template <bool INV>
 __global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap lm, PosMap op,
                           const uint64_t* __restrict__ fold, PeerOut po) {
-    extern __shared__ uint64_t s[];
+    extern __shared__ __align__(16) uint64_t s[];
     const uint32_t limb = lm.pos[blockIdx.x], olimb = op.pos[blockIdx.x], mi = lm.idx[blockIdx.x], N = r.N;
     const ModConst mc = r.mc[mi];
     const Mod m       = make_mod(mc);
-    const uint64_t q = mc.q, twoq = 2 * q;
     const Twiddle* tw = (INV ? r.tw_inv : r.tw_fwd) + (size_t)mi * N;
     for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
         s[i] = in[(size_t)limb * N + i];
@@ -323,60 +355,45 @@ __global__ void ntt_small(RingDev r, const uint64_t* in, uint64_t* out, LimbMap 
     if (!INV) {
         for (uint32_t mm = 1, t = N >> 1; mm < N; mm <<= 1, t >>= 1) {
             for (uint32_t b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
-                uint32_t i = b / t, j = 2 * i * t + (b % t);
-                ct_bfly(s[j], s[j + t], ld_tw(tw + mm + i), m);
+                const uint32_t i = b / t, j = 2 * i * t + (b % t);
+                const Twiddle w  = ld_tw(tw + mm + i);
+                const uint64_t x = csub4i(s[j], m.c4);
+                const uint64_t v = shoup_t(s[j + t], w.w, w.ws, m.nq);
+                s[j]             = x + v;
+                s[j + t]         = x - v + m.c4;
             }
             __syncthreads();
         }
         for (uint32_t i = threadIdx.x; i < N; i += blockDim.x)
-            out[(size_t)olimb * N + i] = canon(s[i], m);
+            out[(size_t)olimb * N + i] = canon8(s[i], m);
     }
     else {
         for (uint32_t mm = N >> 1, t = 1; mm > 1; mm >>= 1, t <<= 1) {
             for (uint32_t b = threadIdx.x; b < (N >> 1); b += blockDim.x) {
-                uint32_t i = b / t, j = 2 * i * t + (b % t);
+                const uint32_t i = b / t, j = 2 * i * t + (b % t);
                 gs_bfly(s[j], s[j + t], ld_tw(tw + mm + i), m);
             }
             __syncthreads();
         }
-        const uint32_t h  = N >> 1;
+        const uint32_t h   = N >> 1;
         const LastConst lc = last_const(mc, fold, blockIdx.x);
         for (uint32_t j = threadIdx.x; j < h; j += blockDim.x) {
-            uint64_t a = s[j] + s[j + h], e = s[j] - s[j + h] + twoq;
-            a = shoup(a, lc.a, lc.as, q);
-            e = shoup(e, lc.b, lc.bs, q);
-            for (uint32_t d = 0; d < (po.n ? po.n : 1u); ++d) {
-                uint64_t* o = po.n ? po.base[d] : out;
+            const uint64_t a = csub4i(shoup2(s[j] + s[j + h], lc.a, lc.as, m.nq), m.q);
+            const uint64_t e = csub4i(shoup2(s[j] - s[j + h] + m.c4, lc.b, lc.bs, m.nq), m.q);
+            for_each_dest(out, po, [&](uint64_t* o) {
                 o[(size_t)olimb * N + j]     = a;
                 o[(size_t)olimb * N + j + h] = e;
-            }
+            });
         }
     }
 }
 
-// the second kernel of a pair works in place on the OUTPUT slab: same moduli, output rows
+// ---- launchers ------------------------------------------------------------------------------------------
 LimbMap on_output(const LimbMap& lm, const PosMap& op) {
     LimbMap o = lm;
     for (uint32_t i = 0; i < lm.n; ++i)
         o.pos[i] = op.pos[i];
     return o;
-}
-template <int A>
-void fwd_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
-    const uint32_t stride = r.N >> A;
-    dim3 g1((stride + 255) / 256, lm.n);
-    ntt_fwd_strided<A><<<g1, 256, 0, st>>>(r.dev(), in, out, lm, op);
-    dim3 g2(r.N / kTile, lm.n);
-    ntt_fwd_tile<false><<<g2, 256, 0, st>>>(r.dev(), out, out, on_output(lm, op), op);
-}
-template <int A>
-void inv_big(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op,
-             const uint64_t* fold, const PeerOut& po, cudaStream_t st) {
-    dim3 g2(r.N / kTile, lm.n);
-    ntt_inv_tile<false><<<g2, 256, 0, st>>>(r.dev(), in, out, lm, op, nullptr, PeerOut{});
-    const uint32_t stride = r.N >> A;
-    dim3 g1((stride + 255) / 256, lm.n);
-    ntt_inv_strided<A><<<g1, 256, 0, st>>>(r.dev(), out, on_output(lm, op), fold, po);
 }
 PosMap default_pos(const LimbMap& lm, const PosMap* out_pos) {
     if (out_pos)
@@ -387,7 +404,141 @@ PosMap default_pos(const LimbMap& lm, const PosMap* out_pos) {
     return p;
 }
 
+template <typename K, typename... Args>
+void launch_cluster(K kernel, int A, uint32_t limbs, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(1u << A, limbs, 1);
+    cfg.blockDim           = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = st;
+    cudaLaunchAttribute at[1];
+    at[0].id               = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1u << A;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs              = at;
+    cfg.numAttrs           = A ? 1 : 0;
+    OFHE_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+// one-time per-kernel attributes (16-CTA clusters are a non-portable size; the inverse needs 64 KiB of dynamic smem)
+template <int A>
+void fwd_cluster(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+    static const bool once = [] {
+        if (A > 3)
+            OFHE_CUDA(cudaFuncSetAttribute(ntt_fwd_cluster<A>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        return true;
+    }();
+    (void)once;
+    launch_cluster(ntt_fwd_cluster<A>, A, lm.n, 0, st, r.dev(), in, out, lm, op);
+}
+template <int A>
+void inv_cluster(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op,
+                 const uint64_t* fold, const PeerOut& po, cudaStream_t st) {
+    constexpr size_t smem = sizeof(uint64_t) * kTile * (A ? 2 : 1);
+    static const bool once = [] {
+        if (A > 3)
+            OFHE_CUDA(cudaFuncSetAttribute(ntt_inv_cluster<A>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        OFHE_CUDA(cudaFuncSetAttribute(ntt_inv_cluster<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return true;
+    }();
+    (void)once;
+    launch_cluster(ntt_inv_cluster<A>, A, lm.n, smem, st, r.dev(), in, out, lm, op, fold, po);
+}
+
+// ---- split path: [strided | tile] kernel pairs over chunks of limbs small enough for the lazy intermediate to
+// stay in L2 between the two kernels (the pair then costs one HBM read and one HBM write per limb)
+// Which decomposition runs for a ring of 2^(12+A) points: 0 = one cluster kernel (one HBM pass, DSMEM exchange),
+// 1 = the [strided | tile] kernel pair through L2.  Chosen from measurements on B200 (profiles/r02c_variants.txt):
+// the cluster-wide barrier costs the 16-CTA cluster more than the second pass through L2 costs the pair, the smaller
+// clusters win or tie in the forward direction.  OFHE_NTT_MODE=cluster|split overrides (measurement switch).
+int ntt_mode(bool fwd, int A) {
+    static const int forced = [] {
+        const char* e = getenv("OFHE_NTT_MODE");
+        return !e ? -1 : (e[0] == 's' ? 1 : 0);
+    }();
+    if (forced >= 0)
+        return forced;
+    return (fwd && A <= 3) ? 0 : 1;
+}
+uint32_t ntt_chunk_limbs(const Ring& r) {
+    static const size_t bytes = [] {
+        const char* e = getenv("OFHE_NTT_CHUNK_MIB");
+        return (size_t)(e ? atoi(e) : 1 << 20) << 20;  // default: no chunking (tails cost more than the L2 misses)
+    }();
+    const uint32_t n = (uint32_t)(bytes / (sizeof(uint64_t) * r.N));
+    return n < 1 ? 1 : n;
+}
+void sub_maps(const LimbMap& lm, const PosMap& op, uint32_t s, uint32_t n, LimbMap& l2, PosMap& o2) {
+    l2.n = n;
+    for (uint32_t i = 0; i < n; ++i) {
+        l2.idx[i] = lm.idx[s + i];
+        l2.pos[i] = lm.pos[s + i];
+        o2.pos[i] = op.pos[s + i];
+    }
+}
+template <int A>
+void fwd_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+    const uint32_t chunk = ntt_chunk_limbs(r);
+    for (uint32_t s = 0; s < lm.n; s += chunk) {
+        LimbMap l2;
+        PosMap o2;
+        sub_maps(lm, op, s, std::min(chunk, lm.n - s), l2, o2);
+        ntt_fwd_strided<A><<<dim3((r.N >> A) / 256, l2.n), 256, 0, st>>>(r.dev(), in, out, l2, o2);
+        ntt_fwd_tile<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), out, on_output(l2, o2));
+    }
+}
+template <int A>
+void inv_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op,
+               const uint64_t* fold, const PeerOut& po, cudaStream_t st) {
+    const uint32_t chunk = ntt_chunk_limbs(r);
+    for (uint32_t s = 0; s < lm.n; s += chunk) {
+        LimbMap l2;
+        PosMap o2;
+        sub_maps(lm, op, s, std::min(chunk, lm.n - s), l2, o2);
+        ntt_inv_tile<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), in, out, l2, o2);
+        ntt_inv_strided<A><<<dim3((r.N >> A) / 256, l2.n), 256, 0, st>>>(r.dev(), out, on_output(l2, o2),
+                                                                          fold ? fold + 4 * (size_t)s : nullptr, po);
+    }
+}
+
 }  // namespace
+
+// diagnostic: resident clusters the device can hold for the forward / inverse cluster kernel of ring dimension 2^logN
+namespace {
+template <int A>
+void occ(int out[2]) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(1u << A, 1024, 1);
+    cfg.blockDim           = dim3(256, 1, 1);
+    cudaLaunchAttribute at[1];
+    at[0].id               = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1u << A;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs              = at;
+    cfg.numAttrs           = 1;
+    if (A > 3) {
+        OFHE_CUDA(cudaFuncSetAttribute(ntt_fwd_cluster<A>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        OFHE_CUDA(cudaFuncSetAttribute(ntt_inv_cluster<A>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
+    const size_t smem = sizeof(uint64_t) * kTile * (A ? 2 : 1);
+    OFHE_CUDA(cudaFuncSetAttribute(ntt_inv_cluster<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.dynamicSmemBytes = 0;
+    OFHE_CUDA(cudaOccupancyMaxActiveClusters(&out[0], ntt_fwd_cluster<A>, &cfg));
+    cfg.dynamicSmemBytes = smem;
+    OFHE_CUDA(cudaOccupancyMaxActiveClusters(&out[1], ntt_inv_cluster<A>, &cfg));
+}
+}  // namespace
+void ntt_cluster_occupancy(uint32_t logN, int out[2]) {
+    out[0] = out[1] = 0;
+    switch ((int)logN - 12) {
+        case 1: occ<1>(out); break;
+        case 2: occ<2>(out); break;
+        case 3: occ<3>(out); break;
+        case 4: occ<4>(out); break;
+        default: break;
+    }
+}
 
 void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
                     const PosMap* out_pos) {
@@ -398,16 +549,14 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
         ntt_small<false><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, nullptr, PeerOut{});
     }
-    else if (r.logN == 12) {
-        ntt_fwd_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op);
-    }
     else {
         switch (r.logN - 12) {
-            case 1: fwd_big<1>(r, in, out, lm, op, st); break;
-            case 2: fwd_big<2>(r, in, out, lm, op, st); break;
-            case 3: fwd_big<3>(r, in, out, lm, op, st); break;
-            case 4: fwd_big<4>(r, in, out, lm, op, st); break;
-            case 5: fwd_big<5>(r, in, out, lm, op, st); break;
+            case 0: fwd_cluster<0>(r, in, out, lm, op, st); break;
+            case 1: ntt_mode(true, 1) ? fwd_split<1>(r, in, out, lm, op, st) : fwd_cluster<1>(r, in, out, lm, op, st); break;
+            case 2: ntt_mode(true, 2) ? fwd_split<2>(r, in, out, lm, op, st) : fwd_cluster<2>(r, in, out, lm, op, st); break;
+            case 3: ntt_mode(true, 3) ? fwd_split<3>(r, in, out, lm, op, st) : fwd_cluster<3>(r, in, out, lm, op, st); break;
+            case 4: ntt_mode(true, 4) ? fwd_split<4>(r, in, out, lm, op, st) : fwd_cluster<4>(r, in, out, lm, op, st); break;
+            case 5: fwd_split<5>(r, in, out, lm, op, st); break;
             default: throw Error("ring dimension above 2^17 is not supported");
         }
     }
@@ -418,22 +567,20 @@ void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
                     const PosMap* out_pos, const uint64_t* fold, const PeerOut* peers) {
     if (lm.n == 0)
         return;
-    const PosMap op = default_pos(lm, out_pos);
+    const PosMap op  = default_pos(lm, out_pos);
     const PeerOut po = peers ? *peers : PeerOut{};
     if (r.logN < 12) {
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
         ntt_small<true><<<lm.n, th, r.N * sizeof(uint64_t), st>>>(r.dev(), in, out, lm, op, fold, po);
     }
-    else if (r.logN == 12) {
-        ntt_inv_tile<true><<<dim3(1, lm.n), 256, 0, st>>>(r.dev(), in, out, lm, op, fold, po);
-    }
     else {
         switch (r.logN - 12) {
-            case 1: inv_big<1>(r, in, out, lm, op, fold, po, st); break;
-            case 2: inv_big<2>(r, in, out, lm, op, fold, po, st); break;
-            case 3: inv_big<3>(r, in, out, lm, op, fold, po, st); break;
-            case 4: inv_big<4>(r, in, out, lm, op, fold, po, st); break;
-            case 5: inv_big<5>(r, in, out, lm, op, fold, po, st); break;
+            case 0: inv_cluster<0>(r, in, out, lm, op, fold, po, st); break;
+            case 1: ntt_mode(false, 1) ? inv_split<1>(r, in, out, lm, op, fold, po, st) : inv_cluster<1>(r, in, out, lm, op, fold, po, st); break;
+            case 2: ntt_mode(false, 2) ? inv_split<2>(r, in, out, lm, op, fold, po, st) : inv_cluster<2>(r, in, out, lm, op, fold, po, st); break;
+            case 3: ntt_mode(false, 3) ? inv_split<3>(r, in, out, lm, op, fold, po, st) : inv_cluster<3>(r, in, out, lm, op, fold, po, st); break;
+            case 4: ntt_mode(false, 4) ? inv_split<4>(r, in, out, lm, op, fold, po, st) : inv_cluster<4>(r, in, out, lm, op, fold, po, st); break;
+            case 5: inv_split<5>(r, in, out, lm, op, fold, po, st); break;
             default: throw Error("ring dimension above 2^17 is not supported");
         }
     }

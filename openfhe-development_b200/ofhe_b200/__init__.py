@@ -54,6 +54,8 @@ SIGNATURES = {
     "ofhe_evk_create": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "ofhe_evk_create_random": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "ofhe_evk_destroy": (None, [_vp]),
+    "ofhe_hks_reserve": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "ofhe_ntt_cluster_occupancy": (C.c_int, [_vp, C.c_uint32, _vp]),
     "ofhe_hks_modup": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "ofhe_hks_inner_product": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_hks_approx_mod_down": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp]),
@@ -112,10 +114,11 @@ def lib():
     """Load libofhe_b200.so (built in-tree by `make -C openfhe-development_b200`); fails loudly if missing."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise OfheError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+        path = os.environ.get("OFHE_B200_LIB", LIB_PATH)  # measurement builds (tools/variants.sh); default: in-tree
+        if not os.path.exists(path):
+            raise OfheError(f"{path} is missing: build it with __graft_entry__.build() "
                             "(there is no CPU fallback for this backend)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)
             f.restype = res
@@ -489,6 +492,10 @@ class Hks:
         if self.h:
             lib().ofhe_hks_destroy(self.h)
             self.h = None
+
+    def reserve(self, sizeQl):
+        """Level tables + this stream's workspace ahead of time (needed before capturing into a CUDA graph)."""
+        _ck(lib().ofhe_hks_reserve(self.h, sizeQl, _stream()))
 
     def num_digits(self, sizeQl):
         return lib().ofhe_hks_num_digits(self.h, sizeQl)
