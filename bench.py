@@ -175,6 +175,40 @@ def cpu_reference_run(steps, warmup, budget_s=150.0):
                 host=dict(logical_cpus=logical, physical_cores=physical)), sec
 
 
+def live_reference_ckks():
+    """The unmodified reference's CKKS context for the bench workload (None if oracle/_ref did not travel)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Reference, reference_available
+
+    if not reference_available():
+        return None
+    ref = Reference()
+    return ref.ckks(CFG["N"], CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
+
+
+def committed_profile_numbers():
+    """Figures that come from profiler captures, read from the tracked files they were summarised into (never literals
+    in this file): DRAM bytes of one roofline-slab forward NTT launch (ncu --set full) and the measured issue cost of
+    one warp-butterfly (tools/ubench/bfly.cu)."""
+    out = dict(traffic=None, traffic_source=None, cycles_per_warp_butterfly=None, cycles_source=None)
+    try:
+        with open(os.path.join(ROOT, "profiles", "ntt_roofline_traffic.json")) as f:
+            t = json.load(f)
+        out["traffic"], out["traffic_source"] = float(t["dram_bytes_per_launch"]), t["source"]
+        out["traffic_limbs"], out["traffic_N"] = int(t["limbs"]), int(t["N"])
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02a_ubench_bfly.txt")) as f:
+            for ln in f:
+                if ln.startswith("V2 fwd"):
+                    out["cycles_per_warp_butterfly"] = float(ln.split("=")[1].split()[0])
+                    out["cycles_source"] = "profiles/r02a_ubench_bfly.txt (V2: shipped forward butterfly, registers only)"
+    except Exception:
+        pass
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,8 +218,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--ref-child", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slots", type=int, default=4, help="N>1: pipeline slots (independent multiplications in flight)")
-    ap.add_argument("--slots1", type=int, default=2, help="N=1: independent multiplications in flight (streams)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the config 1 / 3 / 5 side measurements")
+    ap.add_argument("--slots", type=int, default=4,
+                    help="independent multiplications in flight (streams); the same policy at every GPU count")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N>1: limb exchange by NVLink peer stores fused into the INTT (default) or NCCL all-gathers")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="N>1 push mode: eager launches, no CUDA graphs")
@@ -199,10 +234,11 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(a.steps, 50))
-        base, sec = cpu_reference_run(steps, max(1, min(a.warmup, 2)))
+        steps = max(1, min(a.steps, 10))
+        warm = max(1, min(a.warmup, 2))
+        base, sec = cpu_reference_run(steps, warm)
         line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=steps,
-                    warmup=max(1, min(a.warmup, 2)), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
+                    warmup=warm, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="u64", data="synthetic", config={"workload": WORKLOAD},
                     cpu_baseline=base, e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0,
                                                 d2h_bytes_per_step=0), gpu_launches=0)
@@ -222,10 +258,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     p = m.ckks_paramgen(CFG["N"], CFG["depth"], CFG["scale_bits"], CFG["first_bits"], CFG["dnum"], CFG["scal_tech"])
     N, sizeQ, sizeP, dnum = p["N"], p["sizeQ"], p["sizeP"], p["dnum"]
+    sizeQP = sizeQ + sizeP
     ctx = m.Context(local_rank)
     ring = m.Ring(ctx, N, p["moduli"], p["roots"])
     sizeQl = sizeQ
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_slots = max(1, a.slots)
+    streams = [torch.cuda.Stream() for _ in range(n_slots)]
 
     def barrier():
         if dist is not None:
@@ -238,53 +277,82 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local_rank)
-    if world == 1:
-        hks = m.Hks(ring, sizeQ, sizeP, dnum)
-        evk = m.EvalKey(hks, seed=1234)
-        idx2 = list(range(sizeQl)) * 2
-        ct1, ct2, out = ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N)
-        ring.fill_uniform(ct1.view(2 * sizeQl, N), idx2, 11)
-        ring.fill_uniform(ct2.view(2 * sizeQl, N), idx2, 12)
-        # ---- device-resident throughput ------------------------------------------------------------------------
-        # independent multiplications are issued round-robin on `slots` streams, each slot with its own context
-        # (scratch arena), tables and key copy: the tail of one multiplication's small launches overlaps the next one
-        n_slots = max(1, a.slots1)
-        extra = []
-        slot_objs = [(hks, evk, out)]
-        for s_ in range(1, n_slots):
-            c_s = m.Context(local_rank)
-            r_s = m.Ring(c_s, N, p["moduli"], p["roots"])
-            h_s = m.Hks(r_s, sizeQ, sizeP, dnum)
-            k_s = m.EvalKey(h_s, seed=1234)
-            slot_objs.append((h_s, k_s, ctx.zeros(2, sizeQl, N)))
-            extra += [k_s, h_s, r_s, c_s]
-        streams = [torch.cuda.Stream() for _ in range(n_slots)]
+    def sum_over_ranks(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
+    def timed(run, steps, warm):
+        """W warm-up steps, then exactly `steps` steps between a barrier + synchronize on both sides, CUDA events on
+        the launch stream, max over ranks -> milliseconds."""
+        run(warm)
+        barrier()
+        e0.record()
+        run(steps)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def fan(fn):
+        """run(n): n independent steps issued round-robin over the slot streams (fn(k, slot))."""
         def run(nsteps):
             cur = torch.cuda.current_stream()
             for st in streams:
                 st.wait_stream(cur)
             for k in range(nsteps):
-                h_s, k_s, o_s = slot_objs[k % n_slots]
                 with torch.cuda.stream(streams[k % n_slots]):
-                    h_s.evalmult(sizeQl, ct1, ct2, k_s, o_s)
+                    fn(k, k % n_slots)
             for st in streams:
                 cur.wait_stream(st)
+        return run
 
-        run(max(a.warmup, n_slots))
-        barrier()
-        sampler.start()
-        e0.record()
-        run(a.steps)
-        e1.record()
-        barrier()
-        sampler.stop_flag.set()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        value = a.steps / (ms * 1e-3)
+    sampler = ClockSampler(local_rank)
+    hks = m.Hks(ring, sizeQ, sizeP, dnum)
+    idx2 = list(range(sizeQl)) * 2
+    ct1, ct2 = ctx.zeros(2, sizeQl, N), ctx.zeros(2, sizeQl, N)
+    ring.fill_uniform(ct1.view(2 * sizeQl, N), idx2, 11)
+    ring.fill_uniform(ct2.view(2 * sizeQl, N), idx2, 12)
+    # ---- evaluation key: the reference's own relinearisation key when the live reference travelled (single GPU), so
+    #      that the timed operation can be checked residue for residue against cc->EvalMult; a seeded key otherwise
+    rc = live_reference_ckks() if (world == 1 and rank == 0) else None
+    if rc is not None:
+        assert [int(v) for v in rc.moduli] == [int(v) for v in p["moduli"]], "parameter generation differs from the reference"
+        ka, kb = rc.evalmult_key()
+        evk = m.EvalKey(hks, ka, kb)
+        del ka, kb
+    else:
+        evk = m.EvalKey(hks, seed=1234)  # identical on every rank (device PRNG keyed by (seed, row, column))
+    parity = None
+    closers = []
+    extra_fields = {}
+
+    if world == 1:
+        # ---- device-resident throughput: independent multiplications round-robin on `slots` streams of ONE context /
+        #      ring / key-switch table set / key (per-stream workspace arenas, ofhe_b200.h)
+        outs = [ctx.zeros(2, sizeQl, N) for _ in range(n_slots)]
+        for st in streams:
+            with torch.cuda.stream(st):
+                hks.reserve(sizeQl)
+        run = fan(lambda k, s_: hks.evalmult(sizeQl, ct1, ct2, evk, outs[s_]))
+        run(n_slots)
+        torch.cuda.synchronize()
         for s_ in range(1, n_slots):
-            assert bool((slot_objs[s_][2] == out).all()), "pipeline slots disagree"
-        parallelism, scaling, launches = f"single GPU, {n_slots} independent multiplications in flight", "weak", LAUNCHES_PER_STEP
+            assert bool((outs[s_] == outs[0]).all()), "concurrent streams of one context disagree"
+        # ---- parity gate BEFORE any timing is accepted (SURVEY 8 d): the same inputs and key through the reference
+        if rc is not None:
+            want = rc.evalmult(sizeQl, ctx.download(ct1), ctx.download(ct2))
+            assert bool((ctx.download(outs[0]) == want).all()), "device EvalMult differs from the reference's cc->EvalMult"
+            parity = "bit-exact vs cc->EvalMult of the live unmodified reference (same inputs, same key, full size)"
+            rc.close()
+        else:
+            parity = "reference build absent on this box: cross-stream agreement only"
+        sampler.start()
+        ms = timed(run, a.steps, max(a.warmup, n_slots))
+        sampler.stop_flag.set()
+        value = a.steps / (ms * 1e-3)
+        parallelism, scaling, launches = (f"single GPU, {n_slots} independent multiplications in flight on {n_slots} "
+                                          f"streams of one context"), "weak", LAUNCHES_PER_STEP
         # ---- end to end through the host-buffer entry point (pinned host memory, copies inside the timed region)
         h1 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
         h2 = torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory()
@@ -292,8 +360,6 @@ def main():
         h1.copy_(ct1.cpu())
         h2.copy_(ct2.cpu())
         e2e_steps = max(6, min(a.steps, 32))
-        # the public host-buffer call for a batch of independent multiplications: every step's inputs come from pinned
-        # host memory and every step's result lands in its own pinned host buffer inside the timed region
         hos = [torch.empty(2, sizeQl, N, dtype=torch.int64).pin_memory() for _ in range(min(e2e_steps, 6))]
         hos = [hos[i % len(hos)] for i in range(e2e_steps)]  # results cycle through 6 pinned buffers
         hks.evalmult_host(sizeQl, h1, h2, evk, ho)
@@ -303,29 +369,25 @@ def main():
         hks.evalmult_host_batch(sizeQl, [h1] * e2e_steps, [h2] * e2e_steps, evk, hos)
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        assert bool((ho.cuda() == out).all()), "host-buffer path and device path disagree"
+        assert bool((ho.cuda() == outs[0]).all()), "host-buffer path and device path disagree"
         for hb in (hos[0], hos[-1]):
             assert bool((hb == ho).all()), "pipelined host path disagrees with the single-call host path"
-        closers = extra + [evk, hks]
     else:
-        # ---- limb-sharded across the ranks (SURVEY 8 e): one EvalMult is split by RNS limb; two NCCL all-gathers per
-        #      step (ModUp sources, ModDown P limbs).  Two pipeline slots on two streams let the all-gathers of one
-        #      multiplication overlap the kernels of the next (steps are independent ciphertext pairs).
-        n_slots = max(1, a.slots)
+        # ---- limb-sharded across the ranks (SURVEY 8 e): ONE multiplication is split by RNS limb.  `slots` pipeline
+        #      slots on `slots` streams (independent ciphertext pairs) let one multiplication's exchange overlap
+        #      another's kernels -- the same in-flight policy as the single-GPU run.
         shards = [m.Shard(ring, sizeQ, sizeP, dnum, rank, world) for _ in range(n_slots)]
         info = shards[0].info(sizeQl)
         own_q, own_p = shards[0].owned(sizeQl)
         nq = len(own_q)
         key_idx = [i for i in range(sizeQ) if i % world == rank] + [sizeQ + j for j in own_p]
-        ea, eb = ctx.zeros(dnum, len(key_idx), N), ctx.zeros(dnum, len(key_idx), N)
-        for j in range(dnum):
-            ring.fill_uniform(ea[j], key_idx, 1000 + 2 * j)
-            ring.fill_uniform(eb[j], key_idx, 1001 + 2 * j)
-        ct1, ct2 = ctx.zeros(2, nq, N), ctx.zeros(2, nq, N)
-        ring.fill_uniform(ct1.view(2 * nq, N), own_q * 2, 11)
-        ring.fill_uniform(ct2.view(2 * nq, N), own_q * 2, 12)
+        # this rank's rows of the (identical everywhere) key and inputs
+        sel = torch.tensor(key_idx, device="cuda")
+        ea = evk_rows(m, ctx, hks, evk, dnum, sizeQP, N, 0).index_select(1, sel).contiguous()
+        eb = evk_rows(m, ctx, hks, evk, dnum, sizeQP, N, 1).index_select(1, sel).contiguous()
+        selq = torch.tensor(own_q, device="cuda")
+        s1, s2 = ct1.index_select(1, selq).contiguous(), ct2.index_select(1, selq).contiguous()
         outs = [ctx.zeros(2, nq, N) for _ in range(n_slots)]
-        streams = [torch.cuda.Stream() for _ in range(n_slots)]
 
         def exchange_obj(obj):
             objs = [None] * world
@@ -334,46 +396,33 @@ def main():
 
         graphs = [None] * n_slots
         if a.exchange == "push":
-            # the INTT's last pass stores each rank's rows into every rank's gather buffer over NVLink (CUDA-IPC
-            # mappings), a one-CTA device barrier replaces the collective's completion: no NCCL call on the data path
             pqs = [m.PeerBuffers(ctx, world * info["slots_q"] * N, rank, world, exchange_obj) for _ in range(n_slots)]
             pps = [m.PeerBuffers(ctx, world * 2 * info["slots_p"] * N, rank, world, exchange_obj) for _ in range(n_slots)]
             pfl = m.PeerBuffers(ctx, m.lib().ofhe_peer_flags_words(world, 2 * n_slots), rank, world, exchange_obj)
-            peer_bufs = pqs + pps + [pfl]
+            closers += pqs + pps + [pfl]
             dist.barrier()
 
             def one(s, c1=None, c2=None):
-                shards[s].evalmult_push(sizeQl, ct1 if c1 is None else c1, ct2 if c2 is None else c2, ea, eb, outs[s],
+                shards[s].evalmult_push(sizeQl, s1 if c1 is None else c1, s2 if c2 is None else c2, ea, eb, outs[s],
                                         pqs[s].array, pps[s].array, pfl.array, slot=s)
         else:
             gqs = [ctx.zeros(world, info["slots_q"], N) for _ in range(n_slots)]
             gps = [ctx.zeros(world, 2, info["slots_p"], N) for _ in range(n_slots)]
-            peer_bufs = []
 
             def all_gather(buf):
                 dist.all_gather_into_tensor(buf, buf[rank])  # in place: the send segment is this rank's slice of buf
 
             def one(s, c1=None, c2=None):
-                shards[s].evalmult(sizeQl, ct1 if c1 is None else c1, ct2 if c2 is None else c2, ea, eb, outs[s],
+                shards[s].evalmult(sizeQl, s1 if c1 is None else c1, s2 if c2 is None else c2, ea, eb, outs[s],
                                    gqs[s], gps[s], all_gather)
 
-        def step(k):
-            s = k % n_slots
-            with torch.cuda.stream(streams[s]):
-                if graphs[s] is not None:
-                    graphs[s].replay()
-                else:
-                    one(s)
+        def step(k, s):
+            if graphs[s] is not None:
+                graphs[s].replay()
+            else:
+                one(s)
 
-        def run(nsteps):
-            cur = torch.cuda.current_stream()
-            for st in streams:
-                st.wait_stream(cur)
-            for k in range(nsteps):
-                step(k)
-            for st in streams:
-                cur.wait_stream(st)
-
+        run = fan(step)
         run(max(a.warmup, n_slots))
         if a.exchange == "push" and a.graph:
             # one CUDA graph per pipeline slot (all launches of a multiplication incl. the device barriers, whose epochs
@@ -391,28 +440,61 @@ def main():
                 print(f"[bench] CUDA graph capture failed, eager launches: {ex}", file=sys.stderr)
             torch.cuda.synchronize()
             dist.barrier()
-            run(n_slots)
-        barrier()
+        # ---- parity gate: every rank's owned rows -> rank 0, compared with the UNSHARDED device EvalMult of the same
+        #      inputs and key (itself pinned to the reference by the single-GPU run and tests/)
+        run(n_slots)
+        torch.cuda.synchronize()
+        pad = ctx.zeros(2, info["slots_q"], N)
+        ok = 1
+        for s_ in range(n_slots):
+            pad[:, :nq] = outs[s_]
+            allp = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, allp, dst=0)
+            if rank == 0:
+                if s_ == 0:
+                    want = ctx.zeros(2, sizeQl, N)
+                    hks.evalmult(sizeQl, ct1, ct2, evk, want)
+                    torch.cuda.synchronize()
+                for r_ in range(world):
+                    rows = [i for i in range(sizeQl) if i % world == r_]
+                    if not bool((allp[r_][:, :len(rows)] == want[:, rows]).all()):
+                        ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.broadcast(flag, src=0)
+        assert int(flag.item()) == 1, "limb-sharded EvalMult differs from the unsharded device EvalMult"
+        parity = (f"every rank's rows of all {n_slots} pipeline slots gathered to rank 0: bit-exact vs the unsharded "
+                  f"device EvalMult (same inputs, same key)")
         sampler.start()
-        e0.record()
-        run(a.steps)
-        e1.record()
-        barrier()
+        ms = timed(run, a.steps, max(a.warmup, n_slots))
         sampler.stop_flag.set()
-        ms = max_over_ranks(e0.elapsed_time(e1))
         value = a.steps / (ms * 1e-3)
         how = ("exchange by NVLink peer stores fused into the INTT + device barriers"
                + (", one CUDA graph per slot" if graphs[0] is not None else "")) if a.exchange == "push" \
             else "2 NCCL all-gathers per EvalMult"
         parallelism, scaling = f"RNS limbs sharded over {world} GPUs, {how}, {n_slots} pipeline slots", "strong"
         launches = 18 if a.exchange == "push" else LAUNCHES_PER_STEP
+        if a.exchange == "push":
+            torch.cuda.synchronize()
+            dist.barrier()
+            assert ctx.peer_barrier_timeouts(pfl.local, world, 2 * n_slots) == 0, "device barrier timed out"
+        # ---- the other mode SURVEY 8(e) asks to report: REPLICAS -- every GPU multiplies its own ciphertext pairs
+        #      with a full key copy, no communication (weak scaling of the same operation)
+        routs = [ctx.zeros(2, sizeQl, N) for _ in range(n_slots)]
+        for st in streams:
+            with torch.cuda.stream(st):
+                hks.reserve(sizeQl)
+        rrun = fan(lambda k, s_: hks.evalmult(sizeQl, ct1, ct2, evk, routs[s_]))
+        rms = timed(rrun, a.steps, max(a.warmup, n_slots))
+        extra_fields["replicas"] = dict(value=world * a.steps / (rms * 1e-3), unit=UNIT, scaling="weak",
+                                        note=f"{world} GPUs x independent unsharded EvalMults ({a.steps} per GPU), "
+                                             f"max-over-ranks device time {rms:.3f} ms")
         # ---- end to end: every rank moves its own limb rows host<->device around the sharded multiplication
         h1 = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
         h2 = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
         ho = torch.empty(2, nq, N, dtype=torch.int64).pin_memory()
-        h1.copy_(ct1.cpu())
-        h2.copy_(ct2.cpu())
-        d1, d2 = torch.empty_like(ct1), torch.empty_like(ct2)
+        h1.copy_(s1.cpu())
+        h2.copy_(s2.cpu())
+        d1, d2 = torch.empty_like(s1), torch.empty_like(s2)
         e2e_steps = max(3, min(a.steps, 10))
 
         def e2e_step():
@@ -429,17 +511,13 @@ def main():
         for _ in range(e2e_steps):
             e2e_step()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        closers = shards + peer_bufs
-        if a.exchange == "push":
-            torch.cuda.synchronize()
-            dist.barrier()
-            assert ctx.peer_barrier_timeouts(pfl.local, world, 2 * n_slots) == 0, "device barrier timed out"
+        closers = shards + closers
     ct_bytes = 2 * sizeQl * N * 8
 
     # ---- roofline of the dominant kernel family: forward limb-NTT on a slab larger than L2 ---------------------
-    L = 240  # 240 limbs x 512 KiB = 120 MiB in + out in place; > L2 together with its 60 MiB of twiddles
-    slab = ctx.zeros(L, N)
-    lidx = [i % (sizeQ + sizeP) for i in range(L)]
+    L = 240  # 240 limbs x 512 KiB = 120 MiB in place, > L2; 4 limbs per modulus in modulus-major order (as the key
+    slab = ctx.zeros(L, N)  # switch orders its multi-polynomial launches)
+    lidx = [i // (L // sizeQP) for i in range(L)]
     ring.fill_uniform(slab, lidx, 99)
     for _ in range(3):
         ring.ntt_fwd(slab, slab, lidx)
@@ -454,42 +532,69 @@ def main():
     peak, peak_src = measured_peak_gbs()
     ntt_bytes = 16.0 * N * L
     achieved = ntt_bytes / (ntt_ms * 1e-3) / 1e9
-    # DRAM bytes of exactly this launch (both kernels) from `ncu --set full` (profiles/r01f_ntt240_summary.csv:
-    # dram read + write = 125.9 + 67.7 + 325.3 + 94.8 MB): 2.4x the algorithmic bytes -- the per-tile twiddles (1 MiB per
-    # 0.5 MiB limb) and the intermediate between the two kernels
-    traffic = 613.6e6 if (N == 65536 and L == 240) else None
-    roofline = dict(bound="hbm", kernel="ntt_fwd (ntt_fwd_strided<4> + ntt_fwd_tile)", achieved=achieved, peak=peak,
-                    unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=ntt_bytes, us_per_limb_ntt=ntt_ms * 1e3 / L)
-    # the co-roof that actually binds a 60-bit NTT on sm_100: integer issue on the multiplier pipe,
-    # ~41 cycles per warp-butterfly (6.2 IMAD.WIDE at 4 + ~8 IMAD-class at 2, ncu pipe accounting), 4 sub-partitions per SM
-    sm_mhz = (sampler.summary().get("sm_max_mhz") or 1965.0)
-    logn = N.bit_length() - 1
-    floor_us = (N // 2 * logn / 32.0) * 41.0 / (ctx.sm_count * 4) / sm_mhz
-    roofline["int_issue"] = dict(bound="integer multiplier issue (fmaheavy pipe)", cycles_per_warp_butterfly=41,
-                                 floor_us_per_limb_ntt=floor_us, frac=floor_us / (ntt_ms * 1e3 / L))
+    prof = committed_profile_numbers()
+    traffic = prof["traffic"] if (prof["traffic"] and prof.get("traffic_limbs") == L and prof.get("traffic_N") == N) else None
+    roofline = dict(bound="hbm", kernel="forward limb-NTT (ntt_fwd_strided<4> + ntt_fwd_tile<4>)", achieved=achieved,
+                    peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=prof["traffic_source"],
+                    peak_source=peak_src, algorithmic_bytes_per_launch=ntt_bytes, us_per_limb_ntt=ntt_ms * 1e3 / L)
+    # the co-roof that binds a 60-bit NTT on sm_100: integer issue, measured per warp-butterfly by
+    # tools/ubench/bfly.cu on registers only
+    if prof["cycles_per_warp_butterfly"]:
+        sm_mhz = (sampler.summary().get("sm_max_mhz") or 1965.0)
+        logn = N.bit_length() - 1
+        cyc = prof["cycles_per_warp_butterfly"]
+        floor_us = (N // 2 * logn / 32.0) * cyc / (ctx.sm_count * 4) / sm_mhz
+        roofline["int_issue"] = dict(bound="integer issue (IMAD.WIDE/IMAD + IADD3 pipes), registers-only microbenchmark",
+                                     cycles_per_warp_butterfly=cyc, source=prof["cycles_source"],
+                                     floor_us_per_limb_ntt=floor_us, frac=floor_us / (ntt_ms * 1e3 / L))
+    del slab
 
     line = None
+    aux = None
+    if rank == 0 and not a.no_aux and world == 1:
+        try:
+            aux = aux_measurements(m, torch, ctx)
+        except Exception as ex:  # side measurements never void the headline
+            aux = {"error": repr(ex)}
     if rank == 0:
         base = None
         if not a.no_cpu_baseline and world == 1:  # the CPU arm is timed at N=1 only (the ranks would fight for the cores)
-            base, _ = cpu_reference_run(a.cpu_steps, 1)
+            base, _ = cpu_reference_run(a.cpu_steps, 1, budget_s=90.0)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=ms / a.steps, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="u64",
                     data="synthetic",
                     config={"workload": WORKLOAD, "parallelism": parallelism,
                             "l2": "per-step working set ~0.6 GB (evk 180 MiB + digits 90 MiB + ...) exceeds the 126 MB L2"},
+                    parity_checked=parity,
                     e2e=dict(value=e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=2 * ct_bytes,
                              d2h_bytes_per_step=ct_bytes, steps=e2e_steps),
                     gpu_launches=launches * a.steps, roofline=roofline, cpu_baseline=base,
                     clocks=sampler.summary())
+        line.update(extra_fields)
+        if aux is not None:
+            line["aux"] = aux
         print(json.dumps(line))
-    for o in closers + [ring, ctx]:
+    for o in closers + [evk, hks, ring, ctx]:
         o.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def evk_rows(m, ctx, hks, evk, dnum, sizeQP, N, which):
+    """Device copy [dnum][sizeQP][N] of the key's A (which=0) or B (which=1) vector."""
+    t = ctx.zeros(dnum, sizeQP, N)
+    evk.copy_to(which, t)
+    return t
+
+
+def aux_measurements(m, torch, ctx):
+    """BASELINE.json configs 1, 3 and 5 beside the headline (single GPU): see tools/aux_bench.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import aux_bench
+
+    return aux_bench.run(m, torch, ctx)
 
 
 if __name__ == "__main__":

@@ -142,6 +142,9 @@ int ofhe_hks_table_host(ofhe_hks* hks, int which, uint32_t a, uint32_t b, uint64
 int ofhe_evk_create(ofhe_hks* hks, const uint64_t* a_h, const uint64_t* b_h, ofhe_evk** out);
 /* synthetic key of uniform residues generated on the device (benchmarks: throughput does not depend on the values)  */
 int ofhe_evk_create_random(ofhe_hks* hks, uint64_t seed, ofhe_evk** out);
+/* copies the key's A (which = 0) or B (which = 1) vector, [dnum][sizeQ+sizeP][N], into a device buffer of the caller
+ * (limb-sharded callers slice their rows out of it)                                                                 */
+int ofhe_evk_copy_to_device(const ofhe_evk* evk, int which, uint64_t* dst_d, void* stream);
 void ofhe_evk_destroy(ofhe_evk* evk);
 
 /* a16 KeySwitchHYBRID::EvalKeySwitchPrecomputeCore              pke/lib/keyswitch/keyswitch-hybrid.cpp:314-379

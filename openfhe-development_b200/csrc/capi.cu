@@ -503,6 +503,16 @@ int ofhe_evk_create_random(ofhe_hks* hks, uint64_t seed, ofhe_evk** out) {
         *out = new ofhe_evk{k.release()};
     });
 }
+int ofhe_evk_copy_to_device(const ofhe_evk* evk, int which, uint64_t* dst_d, void* stream) {
+    return guard([&] {
+        OFHE_REQUIRE(evk && dst_d && (which == 0 || which == 1), "evk copy: bad arguments");
+        const EvalKey& k = *evk->k;
+        use(k.hks->ring);
+        const size_t words = (size_t)k.dnum * (k.hks->sizeQ + k.hks->sizeP) * k.hks->ring->N;
+        OFHE_CUDA(cudaMemcpyAsync(dst_d, which == 0 ? k.a_d : k.b_d, words * sizeof(uint64_t), cudaMemcpyDeviceToDevice,
+                                  S(stream)));
+    });
+}
 void ofhe_evk_destroy(ofhe_evk* evk) {
     if (evk) {
         delete evk->k;

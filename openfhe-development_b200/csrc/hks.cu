@@ -117,6 +117,8 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
     lv->map_Ql  = make_map(qlp.data(), sizeQl);
     // ---- ModUp: digit j converts rows [j*alpha, j*alpha+ds) of the INTT'd input into all the other rows of its own
     //      Ql.P slab (complementary partition, rns-cryptoparameters.cpp:252-294, written in place: no assembly copy)
+    // The one forward-NTT launch over every converted row of every digit is ordered MODULUS-major (rows of different
+    // digits that share a modulus are adjacent in the grid): their twiddle rows are fetched from HBM once per launch.
     lv->map_modup_ntt.n = 0;
     for (uint32_t j = 0; j < lv->n_digits; ++j) {
         const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
@@ -129,13 +131,19 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
             if (i < s || i >= s + ds) {
                 di.push_back(qlp[i]);
                 dp.push_back(i);  // row in digit j's own [sizeQlP][N] slab
-                uint32_t n                  = lv->map_modup_ntt.n++;
-                OFHE_REQUIRE(n < (uint32_t)kMaxLimbs && j * sizeQlP + i < 65536, "hks: ModUp exceeds the per-launch limb capacity");
-                lv->map_modup_ntt.idx[n] = (uint16_t)qlp[i];
-                lv->map_modup_ntt.pos[n] = (uint16_t)(j * sizeQlP + i);
             }
         lv->modup.push_back(make_bconv(r, si, sp, di, dp));
     }
+    for (uint32_t i = 0; i < sizeQlP; ++i)
+        for (uint32_t j = 0; j < lv->n_digits; ++j) {
+            const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
+            if (i >= s && i < s + ds)
+                continue;  // the digit's own rows keep the original evaluation-format limbs
+            const uint32_t n = lv->map_modup_ntt.n++;
+            OFHE_REQUIRE(n < (uint32_t)kMaxLimbs && j * sizeQlP + i < 65536, "hks: ModUp exceeds the per-launch limb capacity");
+            lv->map_modup_ntt.idx[n] = (uint16_t)qlp[i];
+            lv->map_modup_ntt.pos[n] = (uint16_t)(j * sizeQlP + i);
+        }
     {   // QHatInv of every source limb folded into the constants of the inverse NTT that precedes the conversion
         std::vector<uint64_t> fold(4 * (size_t)sizeQl);
         for (uint32_t j = 0; j < lv->n_digits; ++j) {
@@ -152,10 +160,10 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
     if (sizeP) {
         const uint64_t* P = r.moduli.data() + sizeQ;
         std::vector<uint64_t> fold(8 * (size_t)sizeP);
-        for (uint32_t b = 0; b < 2; ++b)
-            for (uint32_t j = 0; j < sizeP; ++j) {
+        for (uint32_t j = 0; j < sizeP; ++j)  // launch order of map_P2: modulus-major (j, then polynomial b)
+            for (uint32_t b = 0; b < 2; ++b) {
                 uint64_t w = hm::inv(hm::prod_mod(P, sizeP, (long)j, P[j]), P[j]);
-                make_inv_fold(r, sizeQ + j, w, &fold[4 * (size_t)(b * sizeP + j)]);
+                make_inv_fold(r, sizeQ + j, w, &fold[4 * (size_t)(2 * j + b)]);
             }
         OFHE_CUDA(cudaMalloc(&lv->fold_moddown_d, sizeof(uint64_t) * fold.size()));
         OFHE_CUDA(cudaMemcpy(lv->fold_moddown_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
@@ -174,21 +182,23 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
         lv->moddown = make_bconv(r, si, sp, di, dp);
     }
     // two-polynomial maps used by the batched ModDown
+    // (both in modulus-major launch order: the two polynomials' rows of one modulus are adjacent)
     lv->map_P2.n = 0;
     lv->map_Ql2.n = 0;
-    for (uint32_t b = 0; b < 2; ++b) {
-        for (uint32_t j = 0; j < sizeP; ++j) {
-            uint32_t n        = lv->map_P2.n++;
-            lv->map_P2.idx[n] = (uint16_t)(sizeQ + j);
-            lv->map_P2.pos[n] = (uint16_t)(b * sizeQlP + sizeQl + j);  // P rows of e_b inside [2][sizeQlP][N]
+    for (uint32_t j = 0; j < sizeP; ++j)
+        for (uint32_t b = 0; b < 2; ++b) {
+            uint32_t n           = lv->map_P2.n++;
+            lv->map_P2.idx[n]    = (uint16_t)(sizeQ + j);
+            lv->map_P2.pos[n]    = (uint16_t)(b * sizeQlP + sizeQl + j);  // P rows of e_b inside [2][sizeQlP][N]
+            lv->gather_P2.pos[n] = (uint16_t)(b * sizeP + j);             // -> row of p_tmp [2][sizeP][N]
         }
-        for (uint32_t i = 0; i < sizeQl; ++i) {
+    for (uint32_t i = 0; i < sizeQl; ++i)
+        for (uint32_t b = 0; b < 2; ++b) {
             uint32_t n         = lv->map_Ql2.n++;
             lv->map_Ql2.idx[n] = (uint16_t)i;
             lv->map_Ql2.pos[n] = (uint16_t)(b * sizeQl + i);
             fill_scalar(lv->pinv2, b * sizeQl + i, PInvModq[i], r.moduli[i]);
         }
-    }
     // ---- CKKS rescale constants for dropping limb l = sizeQl-1 (ckksrns-cryptoparameters.cpp:60-83):
     //      A_i = floor(QlInv * Ql / q_l) mod q_i = -q_l^-1 mod q_i (q_i | Ql),  B_i = q_l^-1 mod q_i
     if (sizeQl >= 2) {
@@ -252,10 +262,7 @@ void Hks::mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const
     const size_t N = r.N, sizeQlP = sizeQl + sizeP;
     OFHE_REQUIRE(sizeP >= 1, "ModDown needs a non-empty auxiliary basis");
     // P rows of both polynomials -> coefficient format, gathered into p_tmp [2][sizeP][N]   (dcrtpoly-impl.h:976-984)
-    PosMap gather;
-    for (uint32_t n = 0; n < lv.map_P2.n; ++n)
-        gather.pos[n] = (uint16_t)n;
-    launch_ntt_inv(r, e01, p_tmp, lv.map_P2, st, &gather, lv.fold_moddown_d);  // times PHatInvModp
+    launch_ntt_inv(r, e01, p_tmp, lv.map_P2, st, &lv.gather_P2, lv.fold_moddown_d);  // times PHatInvModp
     // P -> Ql conversion of both polynomials in one launch                                     (:987-988)
     launch_bconv(r, *lv.moddown, p_tmp, conv_tmp, 2, (size_t)sizeP * N, (size_t)sizeQl * N, /*premultiplied=*/true, st);
     // back to EVALUATION                                                                         (:1001)

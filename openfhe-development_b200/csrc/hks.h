@@ -31,6 +31,7 @@ struct Hks {
         LimbMap map_Ql, map_QlP;
         LimbMap map_modup_ntt;  // every converted row of every digit slab
         LimbMap map_P2, map_Ql2;
+        PosMap gather_P2;  // output rows of the ModDown inverse NTT (p_tmp [2][sizeP][N]) in map_P2's launch order
         std::vector<std::unique_ptr<BConv>> modup;
         std::unique_ptr<BConv> moddown;
         uint64_t* fold_modup_d = nullptr;    // [sizeQl][4]: INTT constants with PartQlHatInvModq folded in

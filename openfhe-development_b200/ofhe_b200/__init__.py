@@ -55,6 +55,7 @@ SIGNATURES = {
     "ofhe_evk_create_random": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "ofhe_evk_destroy": (None, [_vp]),
     "ofhe_hks_reserve": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "ofhe_evk_copy_to_device": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "ofhe_ntt_cluster_occupancy": (C.c_int, [_vp, C.c_uint32, _vp]),
     "ofhe_hks_modup": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "ofhe_hks_inner_product": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
@@ -470,6 +471,10 @@ class EvalKey:
         else:
             _ck(lib().ofhe_evk_create_random(hks.h, 0 if seed is None else seed, C.byref(h)))
         self.h = h
+
+    def copy_to(self, which, dst):
+        """A (which=0) / B (which=1) vector -> dst [dnum][sizeQ+sizeP][N] (device tensor)."""
+        _ck(lib().ofhe_evk_copy_to_device(self.h, which, _ptr(dst), _stream()))
 
     def close(self):
         if self.h:

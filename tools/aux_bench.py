@@ -1,0 +1,160 @@
+"""Side measurements printed in bench.py's "aux" object (single GPU): BASELINE.json configs 1, 3 and 5.
+
+  config 1  DCRTPoly SwitchFormat fwd+inv, N = 4096, ONE 60-bit limb: latency of one transform pair (not a batch),
+            eager launches and CUDA-graph replay, next to the reference's own SwitchFormat on one host core
+            (what benchmark/src/poly-benchmark.h:283-299 `Native_avg_ntt_intt` times) -- bit-exact check included
+  config 3  BFV EvalMult (HPSPOVERQ), N = 2^15, 12 Q + 12 R limbs, relinearised: mults/s and the algorithmic-byte
+            roofline of the whole operation
+  config 5  batched NTT sweep N in 2^12..2^17 x L in {1, 8, 64}: algorithmic GB/s (16*N*L per transform) vs HBM peak
+All inputs synthetic; device timing with CUDA events on the launch stream after warm-up.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def _timeit(torch, f, reps, warm=3):
+    for _ in range(warm):
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps  # us
+
+
+def config1(m, torch, ctx):
+    N = 4096
+    q, roots = m.dcrt_params(N, 1, 60)  # ILDCRTParams(2N, 1, 60) as poly-benchmark.h:86 builds it
+    ring = m.Ring(ctx, N, q, roots)
+    x = ctx.zeros(1, N)
+    ring.fill_uniform(x, [0], 5)
+    x0 = x.clone()
+
+    def pair():
+        ring.ntt_fwd(x, x, [0])
+        ring.ntt_inv(x, x, [0])
+
+    eager = _timeit(torch, pair, 200)
+    assert bool((x == x0).all()), "SwitchFormat round trip is not the identity"
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        pair()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(10):
+                pair()
+        graph = _timeit(torch, g.replay, 50) / 10
+    out = {"workload": "DCRTPoly SwitchFormat fwd+inv, N=4096, 1 x 60-bit limb (one polynomial, not a batch)",
+           "gpu_us_per_fwd_inv_pair_eager": eager, "gpu_us_per_fwd_inv_pair_graph": graph}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import Reference, reference_available
+
+        if reference_available():
+            ref = Reference()
+            ref.L.ref_set_threads(1)
+            h = ctx.download(x0)[0].copy()
+            want = h.copy()
+            ref.L.ref_ntt_fwd(int(q[0]), int(roots[0]), N, want)
+            y = x0.clone()
+            ring.ntt_fwd(y, y, [0])
+            out["bit_exact_vs_reference_forward"] = bool((ctx.download(y)[0] == want).all())
+            sec = ref.L.ref_time_switch_format(N, 1, np.ascontiguousarray(q, dtype=np.uint64),
+                                               np.ascontiguousarray(roots, dtype=np.uint64), h.reshape(1, N).copy(), 2000)
+            out["reference_cpu_us_per_fwd_inv_pair_1_thread"] = 2 * sec * 1e6 if sec > 0 else None
+            out["reference_note"] = "DCRTPoly::SwitchFormat of the unmodified reference, 1 thread (the operation " \
+                                    "poly-benchmark's Native_avg_ntt_intt times)"
+    except Exception as ex:
+        out["reference_error"] = repr(ex)
+    ring.close()
+    return out
+
+
+def config3(m, torch, ctx):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bfv_cfg3_tables.npz"))
+    N, nQ, nR = (int(v) for v in g["shape"])
+    sizeP, dnum, _ = (int(v) for v in g["ks_shape"])
+    T = {k[2:]: g[k] for k in g.files if k.startswith("T_")}
+    ring = m.Ring(ctx, N, g["moduli"], g["roots"])
+    mult = m.BfvMult(ring, nQ, nR, T)
+    ring_ks = m.Ring(ctx, N, np.concatenate([g["moduli"][:nQ], g["moduliP"]]),
+                     np.concatenate([g["roots"][:nQ], g["rootsP"]]))
+    hks = m.Hks(ring_ks, nQ, sizeP, dnum)
+    evk = m.EvalKey(hks, seed=3)
+    ct1, ct2, out = ctx.zeros(2, nQ, N), ctx.zeros(2, nQ, N), ctx.zeros(2, nQ, N)
+    ring.fill_uniform(ct1.view(2 * nQ, N), list(range(nQ)) * 2, 1)
+    ring.fill_uniform(ct2.view(2 * nQ, N), list(range(nQ)) * 2, 2)
+    us = _timeit(torch, lambda: mult.evalmult(hks, ct1, ct2, evk, out), 30)
+    limb = 8.0 * N
+    nQR = nQ + nR
+    # algorithmic bytes (SURVEY 8 d accounting, unfused): 4 polys INTT (Q) + expand Q->R (read Q write R) + 4 polys NTT
+    # over QR + tensor (4 in + 3 out over QR) + 3 polys INTT over QR + scale-and-round QR->Q + 3 polys NTT over Q
+    # + hybrid key switch of c2 over Q u P + final adds
+    nb = limb * (4 * 2 * nQ + 4 * (nQ + nR) + 4 * 2 * nQR + 7 * nQR + 3 * 2 * nQR + 3 * (nQR + nQ) + 3 * 2 * nQ)
+    alpha = (nQ + dnum - 1) // dnum
+    nb += limb * (2 * nQ + dnum * ((alpha + (nQ + sizeP - alpha)) + 2 * (nQ + sizeP - alpha))
+                  + (dnum * (nQ + sizeP) + 2 * dnum * (nQ + sizeP) + 2 * (nQ + sizeP))
+                  + 2 * (2 * sizeP + (sizeP + nQ) + 2 * nQ + 3 * nQ) + 2 * 3 * nQ)
+    peak = _peak()
+    res = {"workload": "BFV EvalMult HPSPOVERQ + relinearisation, N=2^15, 12 Q + 12 R limbs (60-bit), HYBRID 4 P limbs dnum 3",
+           "evalmult_relin_us": us, "evalmult_relin_per_s": 1e6 / us,
+           "roofline": {"bound": "hbm", "algorithmic_bytes": nb, "achieved_gbs": nb / us * 1e-3, "peak_gbs": peak,
+                        "frac": nb / us * 1e-3 / peak}}
+    for o in (evk, hks, mult, ring_ks, ring):
+        o.close()
+    return res
+
+
+def config5(m, torch, ctx):
+    peak = _peak()
+    rows = []
+    for logn in (12, 13, 14, 15, 16, 17):
+        N = 1 << logn
+        q, roots = m.dcrt_params(N, 64, 60)
+        ring = m.Ring(ctx, N, q, roots)
+        for L in (1, 8, 64):
+            batch = max(1, min(256 // L, int(np.ceil(160e6 / (8.0 * N * L)))))
+            n = L * batch
+            slab = ctx.zeros(n, N)
+            idx = sorted(list(range(L)) * batch)  # modulus-major
+            ring.fill_uniform(slab, idx, 7)
+
+            def pair():
+                ring.ntt_fwd(slab, slab, idx)
+                ring.ntt_inv(slab, slab, idx)
+
+            us = _timeit(torch, pair, 5, warm=2)
+            gbs = 2 * 16.0 * N * n / us * 1e-3
+            rows.append({"logN": logn, "L": L, "batch": batch, "us_per_dcrt_switchformat": us / (2 * batch),
+                         "gbs": round(gbs, 1), "frac_of_measured_hbm": round(gbs / peak, 4)})
+            del slab
+        ring.close()
+    return {"workload": "batched DCRTPoly SwitchFormat (fwd + inv), 16*N*L algorithmic bytes per transform, slab > L2 "
+                        "where 256 limbs allow", "peak_gbs": peak, "rows": rows}
+
+
+def run(m, torch, ctx):
+    out = {}
+    for name, fn in (("config1_ntt4096_single_limb", config1), ("config3_bfv_evalmult_n15", config3),
+                     ("config5_ntt_sweep", config5)):
+        try:
+            out[name] = fn(m, torch, ctx)
+        except Exception as ex:
+            out[name] = {"error": repr(ex)}
+    return out

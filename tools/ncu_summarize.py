@@ -13,11 +13,11 @@ KEYS = [
     ("launch__registers_per_thread", "regs"),
     ("dram__bytes_read.sum", "dram_read"),
     ("dram__bytes_write.sum", "dram_write"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
-    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "fmaheavy_pct"),
+    ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "fmaheavy_pct"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu_pct"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math_throttle"),
