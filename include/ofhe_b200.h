@@ -44,6 +44,11 @@ int ofhe_memcpy_h2d(ofhe_ctx* ctx, void* dst_d, const void* src_h, size_t bytes,
 int ofhe_memcpy_d2h(ofhe_ctx* ctx, void* dst_h, const void* src_d, size_t bytes, void* stream);
 int ofhe_memcpy_d2d(ofhe_ctx* ctx, void* dst_d, const void* src_d, size_t bytes, void* stream);
 int ofhe_stream_sync(ofhe_ctx* ctx, void* stream);
+/* One stream per calling thread: the reference's callers invoke DCRTPoly methods from inside their own
+ * `omp parallel for` (pke/lib/keyswitch/keyswitch-hybrid.cpp:423, scheme/ckksrns/ckksrns-fhe.cpp:1943); every entry
+ * point below is asynchronous on the stream it is given and keeps its workspace per stream. */
+int ofhe_stream_create(ofhe_ctx* ctx, void** stream_out);
+int ofhe_stream_destroy(ofhe_ctx* ctx, void* stream);
 
 /* ---- ring: replaces ILDCRTParams + the static twiddle caches
  *      ChineseRemainderTransformFTTNat::PreCompute            math/hal/intnat/transformnat-impl.h:714-756
@@ -80,6 +85,10 @@ int ofhe_switch_modulus(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d,
 int ofhe_automorphism(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t n_limbs, uint32_t k,
                       void* stream);
 int ofhe_automorphism_map_host(ofhe_ring* ring, uint32_t k, uint32_t* map_h);
+/*          the COEFFICIENT-format branch of PolyImpl::AutomorphismTransform       poly-impl.h:359-362
+ *          out[jk mod N] = (jk div N odd) ? q - in[j] : in[j]  (plain subtraction: 0 maps to q, as in the reference) */
+int ofhe_automorphism_coeff(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t n_limbs,
+                            const uint32_t* mod_idx_h, uint32_t k, void* stream);
 
 /* ---- a10 DCRTPolyImpl::ApproxSwitchCRTBasis                                 dcrtpoly-impl.h:888-932
  * generic source basis {src_idx} -> target basis {dst_idx} (QHatInvModq / QHatModp are derived from the moduli);

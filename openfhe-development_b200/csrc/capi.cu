@@ -139,6 +139,22 @@ int ofhe_stream_sync(ofhe_ctx* ctx, void* stream) {
         OFHE_CUDA(cudaStreamSynchronize(S(stream)));
     });
 }
+int ofhe_stream_create(ofhe_ctx* ctx, void** stream_out) {
+    return guard([&] {
+        OFHE_REQUIRE(ctx && stream_out, "null argument");
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        cudaStream_t st;
+        OFHE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        *stream_out = (void*)st;
+    });
+}
+int ofhe_stream_destroy(ofhe_ctx* ctx, void* stream) {
+    return guard([&] {
+        OFHE_REQUIRE(ctx && stream, "null argument");
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaStreamDestroy(S(stream)));
+    });
+}
 
 int ofhe_ring_create(ofhe_ctx* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* moduli_h, const uint64_t* roots_h,
                      ofhe_ring** out) {
@@ -244,6 +260,15 @@ int ofhe_automorphism(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, u
         OFHE_REQUIRE((k & 1) && k < 2 * ring->r->N, "automorphism index must be odd and below 2N");
         OFHE_REQUIRE(dst_d != src_d, "automorphism cannot run in place");
         launch_automorphism(*ring->r, dst_d, src_d, ring_automap(ring->r, k, S(stream)), n_limbs, S(stream));
+    });
+}
+int ofhe_automorphism_coeff(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t n_limbs,
+                            const uint32_t* mod_idx_h, uint32_t k, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE((k & 1) && k < 2 * ring->r->N, "automorphism index must be odd and below 2N");
+        OFHE_REQUIRE(dst_d != src_d, "automorphism cannot run in place");
+        launch_automorphism_coeff(*ring->r, dst_d, src_d, k, checked_map(ring->r, n_limbs, mod_idx_h), S(stream));
     });
 }
 int ofhe_automorphism_map_host(ofhe_ring* ring, uint32_t k, uint32_t* map_h) {

@@ -140,6 +140,22 @@ __global__ void __launch_bounds__(256) automorph_kernel(uint32_t N, uint64_t* __
         dst[off + j] = src[off + map[j]];
 }
 
+// COEFFICIENT-format automorphism X -> X^k (poly-impl.h:359-362): out[jk mod N] = (jk div N odd) ? q - in[j] : in[j].
+// The reference subtracts in plain integers, so a zero coefficient with an odd wrap count comes out as q itself, not 0;
+// reproduced here (bit-exactness is the contract).  j -> jk mod N is a bijection for odd k: every word written once.
+__global__ void __launch_bounds__(256) automorph_coeff_kernel(RingDev r, uint64_t* __restrict__ dst,
+                                                               const uint64_t* __restrict__ src, uint32_t k, LimbMap lm) {
+    const uint32_t limb = blockIdx.y;
+    const uint64_t q    = r.mc[lm.idx[limb]].q;
+    const size_t off    = (size_t)lm.pos[limb] * r.N;
+    const uint32_t mask = r.N - 1;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < r.N; j += gridDim.x * blockDim.x) {
+        const uint32_t jk = j * k;
+        const uint64_t v  = src[off + j];
+        dst[off + (jk & mask)] = ((jk >> r.logN) & 1u) ? q - v : v;
+    }
+}
+
 // e0[i] = sum_j D_j[i] * b_j[idx(i)],  e1[i] = sum_j D_j[i] * a_j[idx(i)]: products accumulated in 128 bits
 // (dnum * q^2 < 2^128), one reduction per output word.
 __global__ void __launch_bounds__(256) ks_inner_kernel(RingDev r, uint32_t nd, const uint64_t* __restrict__ digits,
@@ -268,6 +284,13 @@ void launch_automorphism(const Ring& r, uint64_t* dst, const uint64_t* src, cons
     if (n_limbs == 0)
         return;
     automorph_kernel<<<ew_grid(r, n_limbs, r.N), 256, 0, st>>>(r.N, dst, src, map_d);
+    OFHE_CUDA(cudaGetLastError());
+}
+void launch_automorphism_coeff(const Ring& r, uint64_t* dst, const uint64_t* src, uint32_t k, const LimbMap& lm,
+                               cudaStream_t st) {
+    if (lm.n == 0)
+        return;
+    automorph_coeff_kernel<<<ew_grid(r, lm.n, r.N), 256, 0, st>>>(r.dev(), dst, src, k, lm);
     OFHE_CUDA(cudaGetLastError());
 }
 void launch_ks_inner_product(const Ring& r, uint32_t nd, const uint64_t* digits, size_t dstride,

@@ -135,6 +135,9 @@ void launch_mul_scalars(const Ring& r, uint64_t* dst, const uint64_t* a, const S
                         cudaStream_t st);
 void launch_automorphism(const Ring& r, uint64_t* dst, const uint64_t* src, const uint32_t* map_d, uint32_t n_limbs,
                          cudaStream_t st);
+// COEFFICIENT-format automorphism (poly-impl.h:359-362), dst != src
+void launch_automorphism_coeff(const Ring& r, uint64_t* dst, const uint64_t* src, uint32_t k, const LimbMap& lm,
+                               cudaStream_t st);
 void launch_build_automap(uint32_t N, uint32_t logN, uint32_t k, uint32_t* map_d, cudaStream_t st);
 // dst[l] = centred switch of the single limb `src` (modulus index from_idx) into every modulus of lm, times
 // scalar sv[l] (Shoup): the SwitchModulus + scalar multiply of DropLastElementAndScale (dcrtpoly-impl.h:703-705)

@@ -54,71 +54,77 @@ __device__ __forceinline__ void for_each_dest(uint64_t* out, const PeerOut& po, 
 
 // ---- phase B of the forward transform: stages S0 .. S0+11 on the tile held in sm (linear layout on entry) ----
 // FROM_GLOBAL: S0 == 0 (N = 4096), round A reads the canonical input straight from `in`.
-template <int LOGN>
-__device__ __forceinline__ void fwd_tile_rounds(uint64_t* sm, uint64_t (&x)[16], const Twiddle* tw, uint32_t tile,
-                                                const Mod& m, uint32_t t) {
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// `after_first_barrier` runs right behind the first block barrier of the tile (the streaming kernels refill the
+// OTHER staging buffer there: every thread has then finished reading it)
+template <int LOGN, typename Hook = NoHook>
+__device__ __forceinline__ void fwd_tile_rounds(uint64_t* sm, uint64_t (&x)[16], TwWin& w, const Twiddle* tw,
+                                                uint32_t tile, const Mod& m, uint32_t t,
+                                                Hook after_first_barrier = Hook{}) {
     constexpr int S0 = LOGN - 12;
-    const uint32_t bh = t >> 4, bl = t & 15u;
-    // ---- round A: tile bits 11..8, thread t holds c = t + 256k (already in x)
-    prefetch_round(tw, ((1u << S0) + tile) * 16u + bh);
-    ct_round<LOGN, S0, 4>(x, tw, (1u << S0) + tile, m);
+    const uint32_t bh = t >> 4, bl = t & 15u, tb = (1u << S0) + tile;
+    // ---- round A: tile bits 11..8, thread t holds c = t + 256k (already in x); w = tw_preload<false>(tw, tb)
+    ct_round16_df<LOGN, S0>(x, w, tw, tb, m);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[t + 256 * k] = x[k];
+    tw_preload<false>(w, tw, tb * 16u + bh);
     __syncthreads();
+    after_first_barrier();
     // ---- round B: tile bits 7..4, c = (t>>4)*256 + (t&15) + 16k
-    prefetch_round(tw, ((1u << S0) + tile) * 256u + t);
+    prefetch_round(tw, tb * 256u + t);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[bh * 256 + bl + 16 * k];
-    ct_round<LOGN, S0 + 4, 4>(x, tw, ((1u << S0) + tile) * 16u + bh, m);
+    ct_round16_df<LOGN, S0 + 4>(x, w, tw, tb * 16u + bh, m);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[swz(bh * 256 + bl + 16 * k)] = x[k];
+    tw_preload<false>(w, tw, tb * 256u + t);
     __syncthreads();
     // ---- round C: tile bits 3..0, c = 16t + k (128 contiguous bytes per thread)
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[swz(16 * t + k)];
-#if defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 1
-    ct_round<LOGN, S0 + 8, 4>(x, tw, ((1u << S0) + tile) * 256u + (t >> 5), m);  // TIMING EXPERIMENT ONLY (wrong results)
-#elif defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 2
-    ct_round<LOGN, S0 + 8, 4>(x, tw, 1u, m);  // TIMING EXPERIMENT ONLY (wrong results)
-#else
-    ct_round<LOGN, S0 + 8, 4>(x, tw, ((1u << S0) + tile) * 256u + t, m);
-#endif
+    ct_round16_df<LOGN, S0 + 8>(x, w, tw, tb * 256u + t, m);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = canon8(x[k], m);
 }
 // ---- phase B of the inverse transform: stages LOGN-1 .. LOGN-12 (mirror order); on exit thread t holds tile
 // offsets t + 256k.  LAST: N = 4096, round A contains the folded final stage.
-template <bool LAST>
-__device__ __forceinline__ void inv_tile_rounds(uint64_t* sm, uint64_t (&x)[16], const Twiddle* tw, uint32_t tbase,
-                                                const LastConst& lc, const Mod& m, uint32_t t) {
-    // tbase = 2^S0 + tile
+template <bool LAST, typename Hook = NoHook>
+__device__ __forceinline__ void inv_tile_rounds(uint64_t* sm, uint64_t (&x)[16], TwWin& w, const Twiddle* tw,
+                                                uint32_t tbase, const LastConst& lc, const Mod& m, uint32_t t,
+                                                Hook after_first_barrier = Hook{}) {
+    // tbase = 2^S0 + tile; w = tw_preload<true>(tw, tbase * 256 + t)
     const uint32_t bh = t >> 4, bl = t & 15u;
     prefetch_round(tw, tbase * 16u + bh);
-    gs_round<4, false>(x, tw, tbase * 256u + t, lc, m);
+    gs_round16_df<false>(x, w, tw, tbase * 256u + t, lc, m);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[swz(16 * t + k)] = x[k];
+    tw_preload<true>(w, tw, tbase * 16u + bh);
     __syncthreads();
+    after_first_barrier();
     prefetch_round(tw, tbase);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[swz(bh * 256 + bl + 16 * k)];
-    gs_round<4, false>(x, tw, tbase * 16u + bh, lc, m);
+    gs_round16_df<false>(x, w, tw, tbase * 16u + bh, lc, m);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[bh * 256 + bl + 16 * k] = x[k];
+    tw_preload<true>(w, tw, tbase);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = sm[t + 256 * k];
-    gs_round<4, LAST>(x, tw, tbase, lc, m);
+    gs_round16_df<LAST>(x, w, tw, tbase, lc, m);
 }
 
 // phase A register rounds: G independent columns of 2^A strided points each, x[g * 2^A + k]
@@ -187,7 +193,9 @@ __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_cluster(RingDev r,
         for (int k = 0; k < 16; ++k)
             x[k] = sm[t + 256 * k];
     }
-    fwd_tile_rounds<LOGN>(sm, x, tw, c, m, t);
+    TwWin ha;
+    tw_preload<false>(ha, tw, (1u << A) + c);
+    fwd_tile_rounds<LOGN>(sm, x, ha, tw, c, m, t);
     ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst + 16 * t);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -221,7 +229,9 @@ __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_cluster(RingDev r,
         x[2 * k]           = v.x;
         x[2 * k + 1]       = v.y;
     }
-    inv_tile_rounds<A == 0>(sm, x, tw, (1u << A) + c, lc, m, t);
+    TwWin ha;
+    tw_preload<true>(ha, tw, ((1u << A) + c) * 256u + t);
+    inv_tile_rounds<A == 0>(sm, x, ha, tw, (1u << A) + c, lc, m, t);
     if constexpr (A == 0) {
         for_each_dest(out, po, [&](uint64_t* o) {
 #pragma unroll
@@ -286,7 +296,9 @@ __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_tile(RingDev r, ui
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         x[k] = p[t + 256 * k];
-    fwd_tile_rounds<12 + A>(sm, x, tw, tile, m, t);
+    TwWin ha;
+    tw_preload<false>(ha, tw, (1u << A) + tile);
+    fwd_tile_rounds<12 + A>(sm, x, ha, tw, tile, m, t);
     ulonglong2* d2 = reinterpret_cast<ulonglong2*>(p + 16 * t);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
@@ -310,7 +322,9 @@ __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_tile(RingDev r, co
         x[2 * k]           = v.x;
         x[2 * k + 1]       = v.y;
     }
-    inv_tile_rounds<false>(sm, x, tw, (1u << A) + tile, LastConst{}, m, t);
+    TwWin ha;
+    tw_preload<true>(ha, tw, ((1u << A) + tile) * 256u + t);
+    inv_tile_rounds<false>(sm, x, ha, tw, (1u << A) + tile, LastConst{}, m, t);
     uint64_t* o = out + (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -336,6 +350,120 @@ __global__ void __launch_bounds__(256) ntt_inv_strided(RingDev r, uint64_t* data
         for (int k = 0; k < (1 << A); ++k)
             o[off + (size_t)k * stride] = x[k];
     });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming tile kernels: the tile half of the split pair as PERSISTENT CTAs.  CTA b transforms tiles b, b + grid,
+// b + 2 grid, ... of the launch's (limb, tile) list and keeps two 32 KiB staging buffers: while the warps run the
+// twelve stages of one tile, the copy engine fills the other buffer with the next one, so no warp ever sits on a
+// global load with its 80 registers allocated and there is no CTA launch/drain between tiles.
+//   forward: one 32 KiB 1-D TMA bulk copy per tile (cp.async.bulk, completion by mbarrier transaction count); the
+//            radix-16 column read t + 256k of the linear tile is bank-conflict free.
+//   inverse: the first round needs 16 CONTIGUOUS points per thread, which conflicts 8-way in a linear tile, so the
+//            tile is staged by 16-byte cp.async copies (coalesced on the global side) into 128-byte rows whose
+//            eight chunks are XOR-swizzled by the row index; each thread then reads its row with 128-bit loads.
+// The refill of a buffer is issued behind the first block barrier of the FOLLOWING tile (every thread is then done
+// reading it) and has two thirds of a tile's compute time to land.
+constexpr uint32_t kTileBytes = kTile * sizeof(uint64_t);
+
+template <int A>
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_tile_stream(RingDev r, uint64_t* data, LimbMap lm,
+                                                                            uint32_t n_items) {
+    extern __shared__ __align__(1024) uint64_t stg[];  // [2][kTile]
+    __shared__ __align__(8) uint64_t full[2];
+    const uint32_t t = threadIdx.x;
+    auto tile_ptr = [&](uint32_t item) {
+        return data + (size_t)lm.pos[item >> A] * r.N + (size_t)(item & ((1u << A) - 1u)) * kTile;
+    };
+    auto refill = [&](uint32_t item, uint32_t b) {  // one thread
+        mbar_expect_tx(&full[b], kTileBytes);
+        tma_load_1d(stg + b * kTile, tile_ptr(item), kTileBytes, &full[b]);
+    };
+    if (t == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+        if (blockIdx.x < n_items)
+            refill(blockIdx.x, 0);
+    }
+    __syncthreads();
+    uint32_t it = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t b = it & 1u, limb = item >> A, tile = item & ((1u << A) - 1u);
+        uint64_t* sm      = stg + b * kTile;
+        const uint32_t mi = lm.idx[limb];
+        const Mod m       = make_mod(r.mc[mi]);
+        const Twiddle* tw = r.tw_fwd + (size_t)mi * r.N;
+        TwWin ha;
+        tw_preload<false>(ha, tw, (1u << A) + tile);
+        mbar_wait(&full[b], (it >> 1) & 1u);
+        uint64_t x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            x[k] = sm[t + 256 * k];
+        fwd_tile_rounds<12 + A>(sm, x, ha, tw, tile, m, t, [&] {
+            if (t == 0 && item + gridDim.x < n_items)
+                refill(item + gridDim.x, b ^ 1u);
+        });
+        // this thread's generic-proxy accesses to the buffer are ordered before the copy engine's next refill of it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(tile_ptr(item) + 16 * t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            d2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
+    }
+}
+
+template <int A>
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_tile_stream(RingDev r, const uint64_t* in, uint64_t* out,
+                                                                            LimbMap lm, PosMap op, uint32_t n_items) {
+    extern __shared__ __align__(1024) uint64_t stg[];  // [2][kTile]
+    __shared__ __align__(8) uint64_t full[2];
+    const uint32_t t = threadIdx.x;
+    auto refill = [&](uint32_t item, uint32_t b) {  // all threads: chunk j = t + 256c of the tile's 2048 chunks
+        const uint64_t* src = in + (size_t)lm.pos[item >> A] * r.N + (size_t)(item & ((1u << A) - 1u)) * kTile;
+        const uint32_t base = smem_u32(stg + b * kTile);
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+            const uint32_t j = t + 256u * c, row = j >> 3, ch = j & 7u;
+            cp_async16(base + row * 128u + ((ch ^ (row & 7u)) << 4), src + 2 * j);
+        }
+        cp_async_arrive(&full[b]);
+    };
+    if (t == 0) {
+        mbar_init(&full[0], 256);
+        mbar_init(&full[1], 256);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (blockIdx.x < n_items)
+        refill(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t b = it & 1u, limb = item >> A, tile = item & ((1u << A) - 1u);
+        uint64_t* sm      = stg + b * kTile;
+        const uint32_t mi = lm.idx[limb];
+        const Mod m       = make_mod(r.mc[mi]);
+        const Twiddle* tw = r.tw_inv + (size_t)mi * r.N;
+        TwWin ha;
+        tw_preload<true>(ha, tw, ((1u << A) + tile) * 256u + t);
+        mbar_wait(&full[b], (it >> 1) & 1u);
+        uint64_t x[16];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(sm + 16 * t + 2 * (c ^ (t & 7u)));
+            x[2 * c]           = v.x;
+            x[2 * c + 1]       = v.y;
+        }
+        inv_tile_rounds<false>(sm, x, ha, tw, (1u << A) + tile, LastConst{}, m, t, [&] {
+            if (item + gridDim.x < n_items)
+                refill(item + gridDim.x, b ^ 1u);
+        });
+        uint64_t* o = out + (size_t)op.pos[limb] * r.N + (size_t)tile * kTile;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            o[t + 256 * k] = x[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -476,26 +604,59 @@ void sub_maps(const LimbMap& lm, const PosMap& op, uint32_t s, uint32_t n, LimbM
         o2.pos[i] = op.pos[s + i];
     }
 }
+// grid of a streaming launch: every CTA gets the same number of tiles (+-1) and at most OFHE_NTT_MINB CTAs share an SM
+uint32_t stream_grid(const Ring& r, uint32_t n_items) {
+    const uint32_t cap    = (uint32_t)r.ctx->sm_count * OFHE_NTT_MINB;
+    const uint32_t rounds = (n_items + cap - 1) / cap;
+    return (n_items + rounds - 1) / rounds;
+}
+bool ntt_stream() {  // OFHE_NTT_STREAM=0 keeps the one-tile-per-CTA kernels (measurement switch)
+    static const bool on = [] {
+        const char* e = getenv("OFHE_NTT_STREAM");
+        return !e || e[0] != '0';
+    }();
+    return on;
+}
 template <int A>
 void fwd_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+    static const bool once = [] {
+        OFHE_CUDA(cudaFuncSetAttribute(ntt_fwd_tile_stream<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)kTileBytes));
+        return true;
+    }();
+    (void)once;
     const uint32_t chunk = ntt_chunk_limbs(r);
     for (uint32_t s = 0; s < lm.n; s += chunk) {
         LimbMap l2;
         PosMap o2;
         sub_maps(lm, op, s, std::min(chunk, lm.n - s), l2, o2);
         ntt_fwd_strided<A><<<dim3((r.N >> A) / 256, l2.n), 256, 0, st>>>(r.dev(), in, out, l2, o2);
-        ntt_fwd_tile<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), out, on_output(l2, o2));
+        if (ntt_stream()) {
+            const uint32_t items = l2.n << A;
+            ntt_fwd_tile_stream<A><<<stream_grid(r, items), 256, 2 * kTileBytes, st>>>(r.dev(), out, on_output(l2, o2), items);
+        }
+        else
+            ntt_fwd_tile<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), out, on_output(l2, o2));
     }
 }
 template <int A>
 void inv_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op,
                const uint64_t* fold, const PeerOut& po, cudaStream_t st) {
+    static const bool once = [] {
+        OFHE_CUDA(cudaFuncSetAttribute(ntt_inv_tile_stream<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)kTileBytes));
+        return true;
+    }();
+    (void)once;
     const uint32_t chunk = ntt_chunk_limbs(r);
     for (uint32_t s = 0; s < lm.n; s += chunk) {
         LimbMap l2;
         PosMap o2;
         sub_maps(lm, op, s, std::min(chunk, lm.n - s), l2, o2);
-        ntt_inv_tile<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), in, out, l2, o2);
+        if (ntt_stream()) {
+            const uint32_t items = l2.n << A;
+            ntt_inv_tile_stream<A><<<stream_grid(r, items), 256, 2 * kTileBytes, st>>>(r.dev(), in, out, l2, o2, items);
+        }
+        else
+            ntt_inv_tile<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), in, out, l2, o2);
         ntt_inv_strided<A><<<dim3((r.N >> A) / 256, l2.n), 256, 0, st>>>(r.dev(), out, on_output(l2, o2),
                                                                           fold ? fold + 4 * (size_t)s : nullptr, po);
     }

@@ -110,6 +110,45 @@ __device__ __forceinline__ uint64_t shoup_t(uint64_t y, uint64_t w, uint64_t ws,
     return y * w + mulhi_t(y, ws) * nq;
 #endif
 }
+// c + (y * w mod q up to a multiple of q): the addend rides on the first wide product's 64-bit accumulator, so the
+// butterfly's X + v costs no instruction of its own (the sum must stay below 2^64: callers' range bounds)
+#ifndef OFHE_NTT_ACC
+#define OFHE_NTT_ACC 0
+#endif
+__device__ __forceinline__ uint64_t shoup_t_acc(uint64_t y, uint64_t w, uint64_t ws, uint64_t nq, uint64_t c) {
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u64 p01, p10, p11, a;\n\t"
+        ".reg .u32 y0, y1, w0, w1, s0, s1, n0, n1, p01l, p01h, p10l, p10h, p11l, p11h, h0, h1, al, ah;\n\t"
+        "mov.b64 {y0, y1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {s0, s1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "mul.wide.u32 p01, y0, s1;\n\t"
+        "mul.wide.u32 p10, y1, s0;\n\t"
+        "mul.wide.u32 p11, y1, s1;\n\t"
+        "mov.b64 {p01l, p01h}, p01;\n\t"
+        "mov.b64 {p10l, p10h}, p10;\n\t"
+        "mov.b64 {p11l, p11h}, p11;\n\t"
+        "add.cc.u32 h0, p11l, p01h;\n\t"
+        "addc.u32 h1, p11h, 0;\n\t"
+        "add.cc.u32 h0, h0, p10h;\n\t"
+        "addc.u32 h1, h1, 0;\n\t"
+        "mad.wide.u32 a, y0, w0, %5;\n\t"
+        "mov.b64 {al, ah}, a;\n\t"
+        "mad.lo.u32 ah, y0, w1, ah;\n\t"
+        "mad.lo.u32 ah, y1, w0, ah;\n\t"
+        "mov.b64 a, {al, ah};\n\t"
+        "mad.wide.u32 a, h0, n0, a;\n\t"
+        "mov.b64 {al, ah}, a;\n\t"
+        "mad.lo.u32 ah, h0, n1, ah;\n\t"
+        "mad.lo.u32 ah, h1, n0, ah;\n\t"
+        "mov.b64 %0, {al, ah};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(y), "l"(w), "l"(ws), "l"(nq), "l"(c));
+    return r;
+}
 // exact Harvey product, result in [0, 2q) for any y
 __device__ __forceinline__ uint64_t shoup2(uint64_t y, uint64_t w, uint64_t ws, uint64_t nq) {
     return y * w + __umul64hi(y, ws) * nq;
@@ -144,9 +183,15 @@ __device__ __forceinline__ void ct_bfly(uint64_t& X, uint64_t& Y, const Twiddle&
         x = csub4i(x, m.c8);
     if constexpr ((b > 8 ? 8 : b) > lim)
         x = csub4i(x, m.c4);
+#if OFHE_NTT_ACC
+    const uint64_t xv = shoup_t_acc(Y, t.w, t.ws, m.nq, x);  // x + v
+    Y                 = (x + x + m.c4) - xv;                  // x - v + 4q
+    X                 = xv;
+#else
     const uint64_t v = shoup_t(Y, t.w, t.ws, m.nq);
     X                = x + v;
     Y                = x - v + m.c4;
+#endif
 }
 // outputs of the last stage (below 8q) -> [0,q)
 __device__ __forceinline__ uint64_t canon8(uint64_t v, const Mod& m) {
@@ -174,6 +219,71 @@ __device__ __forceinline__ void ct_round(uint64_t* x, const Twiddle* __restrict_
     if constexpr (R > 2) ct_stage<LOGN, S0, R, 2, OFF>(x, tw, tw_base, m);
     if constexpr (R > 3) ct_stage<LOGN, S0, R, 3, OFF>(x, tw, tw_base, m);
     if constexpr (R > 4) ct_stage<LOGN, S0, R, 4, OFF>(x, tw, tw_base, m);
+}
+
+// Radix-16 rounds in DEPTH-FIRST order with a rolling twiddle window.
+// A radix-16 round is a binary tree of 15 nodes (depth D = 0..3, 2^D nodes per depth, node = the butterflies that
+// share one twiddle: 8, 4, 2, 1 of them).  Walking the tree depth-first instead of stage by stage keeps the set of
+// twiddles needed next small, so the loads can run kWin nodes (>= 100 instructions) AHEAD of their use inside the
+// same warp without exceeding the 80-register budget: the first kWin are issued before the block barrier that
+// precedes the round (the 16 points are in shared memory then, their registers free), the others as the window
+// rolls.  Stage-by-stage order made every stage start with a load issued a few instructions before its first use:
+// the ncu source page of the round-2 kernel has 70 % of its long-scoreboard stalls on the first product behind a
+// twiddle load (profiles/r02h_tile_stalls.txt).  asm volatile keeps the loads in program order.
+__device__ __forceinline__ Twiddle ld_tw_pinned(const Twiddle* p) {
+    Twiddle t;
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(t.w), "=l"(t.ws) : "l"(p) : "memory");
+    return t;
+}
+#ifndef OFHE_NTT_DF_FWD
+#define OFHE_NTT_DF_FWD 1  // 0: stage-by-stage order with just-in-time twiddle loads (measurement switch)
+#endif
+#ifndef OFHE_NTT_DF_INV
+#define OFHE_NTT_DF_INV 1
+#endif
+#ifndef OFHE_NTT_WIN
+#define OFHE_NTT_WIN 4
+#endif
+constexpr int kWin = OFHE_NTT_WIN;
+struct TwWin {
+    Twiddle t[kWin];
+};
+// forward (pre-order) and inverse (post-order) walks: depth and node-within-depth of step i
+__device__ constexpr int kCtD[15] = {0, 1, 2, 3, 3, 2, 3, 3, 1, 2, 3, 3, 2, 3, 3};
+__device__ constexpr int kCtG[15] = {0, 0, 0, 0, 1, 1, 2, 3, 1, 2, 4, 5, 3, 6, 7};
+__device__ constexpr int kGsD[15] = {3, 3, 2, 3, 3, 2, 1, 3, 3, 2, 3, 3, 2, 1, 0};
+__device__ constexpr int kGsG[15] = {0, 1, 0, 2, 3, 1, 0, 4, 5, 2, 6, 7, 3, 1, 0};
+template <bool INV>
+__device__ __forceinline__ void tw_preload(TwWin& w, const Twiddle* tw, uint32_t tw_base) {
+    if (INV ? !OFHE_NTT_DF_INV : !OFHE_NTT_DF_FWD)
+        return;
+#pragma unroll
+    for (int i = 0; i < kWin; ++i)
+        w.t[i] = ld_tw_pinned(tw + ((tw_base << (INV ? kGsD[i] : kCtD[i])) + (INV ? kGsG[i] : kCtG[i])));
+}
+template <int LOGN, int S0, int OFF, int I>
+__device__ __forceinline__ void ct_df_step(uint64_t* x, TwWin& w, const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                           const Mod& m) {
+    if constexpr (I < 15) {
+        constexpr int D = kCtD[I], g = kCtG[I], half = 1 << (3 - D);
+        const Twiddle t = w.t[I % kWin];
+        if constexpr (I + kWin < 15)
+            w.t[I % kWin] = ld_tw_pinned(tw + ((tw_base << kCtD[I + kWin]) + kCtG[I + kWin]));
+#pragma unroll
+        for (int l = 0; l < half; ++l)
+            ct_bfly<LOGN, S0 + D>(x[OFF + (g << (4 - D)) + l], x[OFF + (g << (4 - D)) + l + half], t, m);
+        ct_df_step<LOGN, S0, OFF, I + 1>(x, w, tw, tw_base, m);
+    }
+}
+// the window must hold the first kWin twiddles of the walk (tw_preload<false> with the same tw_base)
+template <int LOGN, int S0, int OFF = 0>
+__device__ __forceinline__ void ct_round16_df(uint64_t* x, TwWin& w, const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                              const Mod& m) {
+#if OFHE_NTT_DF_FWD
+    ct_df_step<LOGN, S0, OFF, 0>(x, w, tw, tw_base, m);
+#else
+    ct_round<LOGN, S0, 4, OFF>(x, tw, tw_base, m);
+#endif
 }
 
 // ---- inverse (Gentleman-Sande) ----------------------------------------------------------------------------
@@ -234,6 +344,36 @@ __device__ __forceinline__ void gs_round(uint64_t* x, const Twiddle* __restrict_
     }
 }
 
+// inverse radix-16 round, depth-first (post-order) with the rolling twiddle window (see ct_round16_df)
+template <bool LAST, int OFF, int I>
+__device__ __forceinline__ void gs_df_step(uint64_t* x, TwWin& w, const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                           const LastConst& lc, const Mod& m) {
+    if constexpr (I < 15) {
+        constexpr int D = kGsD[I], g = kGsG[I], half = 1 << (3 - D);
+        if constexpr (LAST && I == 14) {
+            gs_last_stage<4, OFF>(x, lc, m);
+        }
+        else {
+            const Twiddle t = w.t[I % kWin];
+            if constexpr (I + kWin < (LAST ? 14 : 15))
+                w.t[I % kWin] = ld_tw_pinned(tw + ((tw_base << kGsD[I + kWin]) + kGsG[I + kWin]));
+#pragma unroll
+            for (int l = 0; l < half; ++l)
+                gs_bfly(x[OFF + (g << (4 - D)) + l], x[OFF + (g << (4 - D)) + l + half], t, m);
+        }
+        gs_df_step<LAST, OFF, I + 1>(x, w, tw, tw_base, lc, m);
+    }
+}
+template <bool LAST, int OFF = 0>
+__device__ __forceinline__ void gs_round16_df(uint64_t* x, TwWin& w, const Twiddle* __restrict__ tw, uint32_t tw_base,
+                                              const LastConst& lc, const Mod& m) {
+#if OFHE_NTT_DF_INV
+    gs_df_step<LAST, OFF, 0>(x, w, tw, tw_base, lc, m);
+#else
+    gs_round<4, LAST, OFF>(x, tw, tw_base, lc, m);
+#endif
+}
+
 // ---- cluster / distributed shared memory primitives (sm_90+) ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -259,6 +399,50 @@ __device__ __forceinline__ void cluster_arrive() {
 }
 __device__ __forceinline__ void cluster_wait() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- asynchronous staging: mbarrier + 1-D TMA bulk copies (UBLKCP) and 16-byte cp.async (LDGSTS) ------------
+// The streaming tile kernels keep two 32 KiB tiles per CTA in flight: the copy engine fills one while the warps
+// transform the other, so no warp ever waits on a global load with its registers allocated.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// spins (hardware-suspended try_wait) until the phase with the given parity has completed; a copy that never lands
+// (a bug) traps after ~2 s instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done    = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!done && spins > 400)
+            __trap();
+    }
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both sides 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// this thread's earlier cp.async copies arrive on `bar` when they have landed (counts towards the expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace nttc

@@ -1,0 +1,124 @@
+// b200-runtime.h -- process-wide state of the B200 lattice backend: the device context, the rings (device-resident
+// twiddle tables) of every CRT basis the host code has used, cached base-conversion tables, and ONE CUDA stream plus
+// grow-only device slabs PER CALLING THREAD.
+//
+// Everything here goes through the C ABI of include/ofhe_b200.h; this header is compiled by the reference's own
+// translation units (g++, no CUDA headers) when they are built with the overlay include directory
+// openfhe-development_b200/hal first on the include path (oracle/Makefile.hal).
+//
+// Threading contract (SURVEY.md section 8 b): the reference calls DCRTPoly methods from inside its own
+// `#pragma omp parallel for` regions (src/pke/lib/scheme/ckksrns/ckksrns-fhe.cpp:1943,
+// src/pke/lib/keyswitch/keyswitch-hybrid.cpp:423).  Each thread therefore owns a stream and its slabs
+// (thread_local); the registries are guarded by a mutex and hand out immutable objects.
+#ifndef LBCRYPTO_INC_LATTICE_HAL_B200_RUNTIME_H
+#define LBCRYPTO_INC_LATTICE_HAL_B200_RUNTIME_H
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ofhe_b200.h"
+#include "utils/exception.h"
+
+namespace lbcrypto {
+namespace b200 {
+
+inline void Check(int rc, const char* what) {
+    if (rc != 0)
+        OPENFHE_THROW(std::string("b200 backend: ") + what + ": " + ofhe_last_error());
+}
+
+// statistics the tests read back to prove that the device path (and not the host mirror) did the work
+struct Counters {
+    uint64_t ntt = 0, ew = 0, automorph = 0, bconv = 0, rescale = 0, moddown = 0, modup = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+class Runtime {
+public:
+    static Runtime& Get() {
+        static Runtime r;
+        return r;
+    }
+    ofhe_ctx* ctx = nullptr;
+
+    // ---- rings: one per ordered list of (modulus, root) pairs over a ring dimension -------------------------
+    ofhe_ring* Ring(uint32_t N, const std::vector<uint64_t>& moduli, const std::vector<uint64_t>& roots) {
+        std::string key(reinterpret_cast<const char*>(&N), sizeof N);
+        key.append(reinterpret_cast<const char*>(moduli.data()), moduli.size() * 8);
+        std::lock_guard<std::mutex> g(mu_);
+        auto it = rings_.find(key);
+        if (it != rings_.end())
+            return it->second;
+        ofhe_ring* r = nullptr;
+        Check(ofhe_ring_create(ctx, N, (uint32_t)moduli.size(), moduli.data(), roots.data(), &r), "ofhe_ring_create");
+        rings_.emplace(std::move(key), r);
+        return r;
+    }
+
+    // ---- base-conversion tables, keyed by the bytes of the tables themselves ----------------------------------
+    // (the reference passes its precomputed vectors by const reference on every call; equal bytes = equal table)
+    ofhe_bconv* BConv(const std::string& key, const std::function<ofhe_bconv*()>& make) {
+        std::lock_guard<std::mutex> g(mu_);
+        auto it = bconvs_.find(key);
+        if (it != bconvs_.end())
+            return it->second;
+        ofhe_bconv* t = make();
+        bconvs_.emplace(key, t);
+        return t;
+    }
+
+    // ---- per-thread stream and slabs --------------------------------------------------------------------------
+    struct Local {
+        void* stream = nullptr;
+        uint64_t* slab[4] = {nullptr, nullptr, nullptr, nullptr};
+        size_t words[4]   = {0, 0, 0, 0};
+        Counters n;
+        ~Local() {
+            // device memory and the stream die with the context at process exit; threads of an OpenMP pool outlive
+            // every DCRTPoly, so nothing is released here
+        }
+    };
+    Local& Mine() {
+        thread_local Local l;
+        if (!l.stream)
+            Check(ofhe_stream_create(ctx, &l.stream), "ofhe_stream_create");
+        return l;
+    }
+    uint64_t* Slab(Local& l, int which, size_t words) {
+        if (l.words[which] < words) {
+            if (l.slab[which]) {
+                Check(ofhe_stream_sync(ctx, l.stream), "ofhe_stream_sync");
+                Check(ofhe_free(ctx, l.slab[which]), "ofhe_free");
+            }
+            void* p = nullptr;
+            Check(ofhe_malloc(ctx, words * sizeof(uint64_t), &p), "ofhe_malloc");
+            l.slab[which]  = static_cast<uint64_t*>(p);
+            l.words[which] = words;
+        }
+        return l.slab[which];
+    }
+    // sum of the counters of the calling thread (tests run the device path single-threaded when they read this)
+    const Counters& MyCounters() {
+        return Mine().n;
+    }
+
+private:
+    Runtime() {
+        const char* dev = std::getenv("OFHE_B200_DEVICE");
+        Check(ofhe_ctx_create(dev ? std::atoi(dev) : 0, &ctx), "ofhe_ctx_create (no CUDA device: this backend has no CPU path)");
+    }
+    ~Runtime() = default;  // process exit tears the CUDA context down
+    std::mutex mu_;
+    std::map<std::string, ofhe_ring*> rings_;
+    std::map<std::string, ofhe_bconv*> bconvs_;
+};
+
+}  // namespace b200
+}  // namespace lbcrypto
+
+#endif

@@ -31,6 +31,8 @@ SIGNATURES = {
     "ofhe_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ofhe_memcpy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ofhe_stream_sync": (C.c_int, [_vp, _vp]),
+    "ofhe_stream_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ofhe_stream_destroy": (C.c_int, [_vp, _vp]),
     "ofhe_ring_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp)]),
     "ofhe_ring_destroy": (None, [_vp]),
     "ofhe_ring_twiddles_host": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _u64p, _u64p]),
@@ -40,6 +42,7 @@ SIGNATURES = {
     "ofhe_ew_mul_scalars": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
     "ofhe_switch_modulus": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "ofhe_automorphism": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "ofhe_automorphism_coeff": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp]),
     "ofhe_automorphism_map_host": (C.c_int, [_vp, C.c_uint32, _vp]),
     "ofhe_approx_switch_crt_basis": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_bconv_create": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp, C.c_int, _vp, _vp, C.POINTER(_vp)]),
