@@ -13,8 +13,11 @@
 #ifndef LBCRYPTO_INC_LATTICE_HAL_B200_RUNTIME_H
 #define LBCRYPTO_INC_LATTICE_HAL_B200_RUNTIME_H
 
+#include <atomic>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -35,7 +38,8 @@ inline void Check(int rc, const char* what) {
 
 // statistics the tests read back to prove that the device path (and not the host mirror) did the work
 struct Counters {
-    uint64_t ntt = 0, ew = 0, automorph = 0, bconv = 0, rescale = 0, moddown = 0, modup = 0, h2d_bytes = 0, d2h_bytes = 0;
+    std::atomic<uint64_t> ntt{0}, ew{0}, automorph{0}, bconv{0}, rescale{0}, moddown{0}, modup{0}, h2d_bytes{0},
+        d2h_bytes{0};
 };
 
 class Runtime {
@@ -77,7 +81,6 @@ public:
         void* stream = nullptr;
         uint64_t* slab[4] = {nullptr, nullptr, nullptr, nullptr};
         size_t words[4]   = {0, 0, 0, 0};
-        Counters n;
         ~Local() {
             // device memory and the stream die with the context at process exit; threads of an OpenMP pool outlive
             // every DCRTPoly, so nothing is released here
@@ -102,9 +105,12 @@ public:
         }
         return l.slab[which];
     }
-    // sum of the counters of the calling thread (tests run the device path single-threaded when they read this)
-    const Counters& MyCounters() {
-        return Mine().n;
+    // process-wide tallies of the device work issued through this backend; OFHE_B200_HAL_STATS=1 prints them at exit
+    // (the GPU tests read that line to prove the reference's suites ran on the device path, not on the mirror)
+    Counters n;
+    // primitive 2N-th root of unity of q when the caller's parameter object carries none (RootOfUnity, nbtheory-impl.h:183-231)
+    static uint64_t RootOr(uint64_t root, uint32_t N, uint64_t q) {
+        return root ? root : ofhe_root_of_unity(2ull * N, q);
     }
 
 private:
@@ -112,7 +118,15 @@ private:
         const char* dev = std::getenv("OFHE_B200_DEVICE");
         Check(ofhe_ctx_create(dev ? std::atoi(dev) : 0, &ctx), "ofhe_ctx_create (no CUDA device: this backend has no CPU path)");
     }
-    ~Runtime() = default;  // process exit tears the CUDA context down
+    ~Runtime() {  // process exit tears the CUDA context down
+        if (std::getenv("OFHE_B200_HAL_STATS"))
+            std::fprintf(stderr,
+                         "[ofhe_b200 hal] device work: limb_ntt=%llu ew_limbs=%llu automorph_limbs=%llu bconv=%llu "
+                         "rescale=%llu modup=%llu moddown=%llu h2d_bytes=%llu d2h_bytes=%llu\n",
+                         (unsigned long long)n.ntt, (unsigned long long)n.ew, (unsigned long long)n.automorph,
+                         (unsigned long long)n.bconv, (unsigned long long)n.rescale, (unsigned long long)n.modup,
+                         (unsigned long long)n.moddown, (unsigned long long)n.h2d_bytes, (unsigned long long)n.d2h_bytes);
+    }
     std::mutex mu_;
     std::map<std::string, ofhe_ring*> rings_;
     std::map<std::string, ofhe_bconv*> bconvs_;

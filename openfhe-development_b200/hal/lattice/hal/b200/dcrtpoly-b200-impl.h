@@ -32,17 +32,17 @@ struct Op {
     void Up(uint64_t* d, const std::vector<Tower>& t, size_t first, size_t count) {
         for (size_t i = 0; i < count; ++i)
             Check(ofhe_memcpy_h2d(rt.ctx, d + i * N, &t[first + i].GetValues()[0], (size_t)N * 8, l.stream), "h2d");
-        l.n.h2d_bytes += count * (size_t)N * 8;
+        rt.n.h2d_bytes += count * (size_t)N * 8;
     }
     void Up1(uint64_t* d, const Tower& t) {
         Check(ofhe_memcpy_h2d(rt.ctx, d, &t.GetValues()[0], (size_t)N * 8, l.stream), "h2d");
-        l.n.h2d_bytes += (size_t)N * 8;
+        rt.n.h2d_bytes += (size_t)N * 8;
     }
     // towers must own N-word value vectors (constructed with initializeElementToZero = true, or copies)
     void Down(const uint64_t* d, std::vector<Tower>& t, size_t first, size_t count) {
         for (size_t i = 0; i < count; ++i)
             Check(ofhe_memcpy_d2h(rt.ctx, &t[first + i][0], d + i * N, (size_t)N * 8, l.stream), "d2h");
-        l.n.d2h_bytes += count * (size_t)N * 8;
+        rt.n.d2h_bytes += count * (size_t)N * 8;
     }
     void Sync() {
         Check(ofhe_stream_sync(rt.ctx, l.stream), "sync");
@@ -53,7 +53,8 @@ inline void Collect(const std::vector<Tower>& towers, size_t first, size_t count
                     std::vector<uint64_t>& root) {
     for (size_t i = 0; i < count; ++i) {
         mod.push_back(towers[first + i].GetModulus().ConvertToInt());
-        root.push_back(towers[first + i].GetRootOfUnity().ConvertToInt());
+        root.push_back(Runtime::RootOr(towers[first + i].GetRootOfUnity().ConvertToInt(),
+                                       towers[first + i].GetParams()->GetRingDimension(), mod.back()));
     }
 }
 template <typename P>
@@ -62,7 +63,7 @@ inline void CollectParams(const std::shared_ptr<P>& params, size_t count, std::v
     const auto& ps = params->GetParams();
     for (size_t i = 0; i < count; ++i) {
         mod.push_back(ps[i]->GetModulus().ConvertToInt());
-        root.push_back(ps[i]->GetRootOfUnity().ConvertToInt());
+        root.push_back(Runtime::RootOr(ps[i]->GetRootOfUnity().ConvertToInt(), ps[i]->GetRingDimension(), mod.back()));
     }
 }
 inline std::vector<uint32_t> Iota(uint32_t first, uint32_t count) {
@@ -138,9 +139,17 @@ B200T void B200C::SwitchFormat(uint32_t) {
     auto& towers      = m_h.GetAllElements();
     const uint32_t L  = (uint32_t)towers.size();
     const Format from = m_h.GetFormat(), to = (from == Format::EVALUATION) ? Format::COEFFICIENT : Format::EVALUATION;
-    m_h.OverrideFormat(to);
-    if (L == 0)
+    if (L == 0) {
+        m_h.OverrideFormat(to);
         return;
+    }
+    if (m_h.GetParams()->GetCyclotomicOrder() != 2 * m_h.GetParams()->GetRingDimension()) {
+        // arbitrary (non power-of-two) cyclotomics are outside this backend's scope (the RNS
+        // schemes only use power-of-two rings); the mirror's Bluestein transform serves them as in the reference
+        m_h.SwitchFormat();
+        return;
+    }
+    m_h.OverrideFormat(to);
     detail::Op op(m_h.GetParams()->GetRingDimension());
     std::vector<uint64_t> mod, root;
     detail::Collect(towers, 0, L, mod, root);
@@ -155,7 +164,7 @@ B200T void B200C::SwitchFormat(uint32_t) {
     op.Down(d, towers, 0, L);
     op.Sync();
     detail::SetFormats(towers, 0, L, to);
-    op.l.n.ntt += L;
+    op.rt.n.ntt += L;
 }
 
 // ---- a9  Plus / Minus / Times / Negate and the Eq forms (dcrtpoly.h:130-190, dcrtpoly-impl.h:347-621):
@@ -198,7 +207,7 @@ inline void Binop(int opc, const Host& a, const Host* b, Host& dst) {
     Check(ofhe_ew_binop(ring, opc, da, da, db, L, idx.data(), op.l.stream), "ofhe_ew_binop");
     op.Down(da, dst.GetAllElements(), 0, L);
     op.Sync();
-    op.l.n.ew += L;
+    op.rt.n.ew += L;
 }
 }  // namespace detail
 
@@ -261,7 +270,7 @@ inline Host TimesScalars(const Host& a, const std::vector<NativeInteger>& s, uin
     Check(ofhe_ew_mul_scalars(ring, d, d, w.data(), L, idx.data(), op.l.stream), "ofhe_ew_mul_scalars");
     op.Down(d, r.GetAllElements(), 0, L);
     op.Sync();
-    op.l.n.ew += L;
+    op.rt.n.ew += L;
     return r;
 }
 }  // namespace detail
@@ -305,7 +314,7 @@ B200T B200C B200C::AutomorphismTransform(uint32_t k) const {
     }
     op.Down(dst, r.GetAllElements(), 0, L);
     op.Sync();
-    op.l.n.automorph += L;
+    op.rt.n.automorph += L;
     return r;
 }
 
@@ -333,7 +342,7 @@ inline uint64_t* DroppedTowerEverywhere(Op& op, ofhe_ring* ring, const Host& h, 
         Check(ofhe_ew_mul_scalars(ring, sw, sw, post->data(), last, idx.data(), op.l.stream), "ofhe_ew_mul_scalars");
     if (h.GetFormat() == Format::EVALUATION)
         Check(ofhe_ntt_fwd(ring, sw, sw, last, idx.data(), op.l.stream), "ofhe_ntt_fwd");
-    op.l.n.ntt += L;
+    op.rt.n.ntt += L;
     return sw;
 }
 }  // namespace detail
@@ -363,7 +372,7 @@ B200T void B200C::DropLastElementAndScale(const std::vector<NativeInteger>& QlQl
     op.Sync();
     if (f == Format::COEFFICIENT)
         detail::SetFormats(m_h.GetAllElements(), 0, L - 1, Format::EVALUATION);
-    op.l.n.rescale += 1;
+    op.rt.n.rescale += 1;
 }
 
 B200T void B200C::ModReduce(const NativeInteger& t, const std::vector<NativeInteger>&, const NativeInteger& negtInvModq,
@@ -389,7 +398,7 @@ B200T void B200C::ModReduce(const NativeInteger& t, const std::vector<NativeInte
     m_h.DropLastElement();
     op.Down(x, m_h.GetAllElements(), 0, L - 1);
     op.Sync();
-    op.l.n.rescale += 1;
+    op.rt.n.rescale += 1;
 }
 
 // ---- a10  ApproxSwitchCRTBasis (:888-932): [sizeQ x N] residues -> [sizeP x N], format label carried over
@@ -413,7 +422,7 @@ B200T B200C B200C::ApproxSwitchCRTBasis(const std::shared_ptr<Params>& paramsQ, 
     Check(ofhe_bconv_apply(tbl, in, out, op.l.stream), "ofhe_bconv_apply");
     op.Down(out, ans.GetAllElements(), 0, sizeP);
     op.Sync();
-    op.l.n.bconv += 1;
+    op.rt.n.bconv += 1;
     return ans;
 }
 
@@ -461,8 +470,8 @@ B200T void B200C::ApproxModUp(const std::shared_ptr<Params>& paramsQ, const std:
     Host qp(paramsQP, Format::EVALUATION, false);
     qp.GetAllElements() = std::move(all);
     m_h                 = std::move(qp);
-    op.l.n.modup += 1;
-    op.l.n.ntt += sizeP + sizeQ;
+    op.rt.n.modup += 1;
+    op.rt.n.ntt += sizeP + sizeQ;
 }
 
 // ---- a11  ApproxModDown (:966-1005), CKKS/BFV (t == 0) and BGV (t > 0) branches
@@ -511,8 +520,8 @@ B200T B200C B200C::ApproxModDown(const std::shared_ptr<Params>& paramsQ, const s
         ans.DropLastElements(diffQ);
     op.Down(q, ans.GetAllElements(), 0, sizeQ);
     op.Sync();
-    op.l.n.moddown += 1;
-    op.l.n.ntt += sizeP + sizeQ;
+    op.rt.n.moddown += 1;
+    op.rt.n.ntt += sizeP + sizeQ;
     return ans;
 }
 
@@ -538,7 +547,7 @@ B200T B200C B200C::SwitchCRTBasis(const std::shared_ptr<Params>& paramsP, const 
     Check(ofhe_bconv_apply(tbl, in, out, op.l.stream), "ofhe_bconv_apply");
     op.Down(out, ans.GetAllElements(), 0, sizeP);
     op.Sync();
-    op.l.n.bconv += 1;
+    op.rt.n.bconv += 1;
     return ans;
 }
 
@@ -643,7 +652,7 @@ B200T B200C B200C::ScaleAndRound(const std::shared_ptr<Params>& paramsOutput,
     Check(ofhe_bconv_apply(t, in, out, op.l.stream), "ofhe_bconv_apply");
     op.Down(out, ans.GetAllElements(), 0, sizeO);
     op.Sync();
-    op.l.n.bconv += 1;
+    op.rt.n.bconv += 1;
     return ans;
 }
 
@@ -683,7 +692,7 @@ B200T B200C B200C::ApproxScaleAndRound(const std::shared_ptr<Params>& paramsP,
     Check(ofhe_bconv_apply(t, in, out, op.l.stream), "ofhe_bconv_apply");
     op.Down(out, ans.GetAllElements(), 0, sizeP);
     op.Sync();
-    op.l.n.bconv += 1;
+    op.rt.n.bconv += 1;
     return ans;
 }
 
@@ -714,7 +723,7 @@ B200T void B200C::ScaleAndRoundPOverQ(const std::shared_ptr<Params>& paramsQ, co
     m_h                = std::move(q);
     op.Down(x, m_h.GetAllElements(), 0, L - 1);
     op.Sync();
-    op.l.n.ew += L - 1;
+    op.rt.n.ew += L - 1;
 }
 
 #undef B200T
