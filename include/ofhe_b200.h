@@ -261,8 +261,12 @@ int ofhe_shard_evalmult_b_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* e
                                uint64_t* const* gatherQ_of_rank_h, uint64_t* const* gatherP_of_rank_h, void* stream);
 /* flags buffers: ofhe_peer_flags_words(world, n_barriers) zero-initialised words per rank.  The kernel bumps this
  * rank's epoch for barrier `index`, publishes it to every rank (release, system scope) and waits until every rank's
- * arrival for that epoch is visible (acquire).  A wait longer than ~10 s gives up and counts a timeout (readable with
- * ofhe_peer_barrier_timeouts) instead of hanging the GPU.                                                            */
+ * arrival for that epoch is visible (acquire).  A wait longer than 10 s of wall clock (%globaltimer) counts a timeout
+ * (readable with ofhe_peer_barrier_timeouts) and then ABORTS this rank's CUDA context (__trap): the phases behind the
+ * barrier would otherwise consume partially written gather buffers and return a silently wrong ciphertext; after the
+ * abort every later CUDA call of the rank fails.  `index` must be below the n_barriers the flags were sized for.  The
+ * spin needs the barrier kernels of all slots to be co-resident: one hardware queue per stream
+ * (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams in flight), as bench.py and tests/conftest.py set it.            */
 size_t ofhe_peer_flags_words(uint32_t world, uint32_t n_barriers);
 int ofhe_peer_barrier(ofhe_ctx* ctx, uint64_t* const* flags_of_rank_h, uint32_t world, uint32_t rank, uint32_t index,
                       void* stream);
@@ -307,13 +311,18 @@ int ofhe_bfv_evalmult(ofhe_bfv* b, ofhe_hks* hks, const uint64_t* ct1_d, const u
  *      scan : shape_out = (N, n_towers, format 0 EVALUATION / 1 COEFFICIENT); per tower its modulus, root of unity and
  *             the byte offset of its N raw words inside the buffer (any output array may be NULL).
  *      write: the byte-identical archive for [n_towers][N] host words (what the reference's Deserialize expects).
- *      upload: scan + one asynchronous host-to-device copy per tower, archive -> dst_d [n_towers][N] (no host DCRTPoly). */
+ *      upload: scan + one asynchronous host-to-device copy per tower, archive -> dst_d [n_towers][N] (no host DCRTPoly).
+ *              The archive is UNTRUSTED: it is rejected unless its ring dimension equals the target ring's, it has at
+ *              most max_towers towers and tower t's modulus equals the ring's modulus mod_idx_h[t] (t when NULL), so a
+ *              slab sized for the ring can never be overrun; check_residues != 0 additionally scans the payload for
+ *              residues >= modulus (the kernels assume canonical inputs).                                            */
 int ofhe_cereal_dcrtpoly_scan(const void* buf_h, size_t len, uint32_t max_towers, uint32_t* shape_out,
                               uint64_t* moduli_out, uint64_t* roots_out, size_t* offsets_out);
 int ofhe_cereal_dcrtpoly_write(uint32_t N, uint32_t n_towers, const uint64_t* moduli_h, const uint64_t* roots_h,
                                uint32_t format, const uint64_t* data_h, void* out_h, size_t cap, size_t* written_out);
-int ofhe_dcrtpoly_upload_cereal(ofhe_ctx* ctx, const void* buf_h, size_t len, uint32_t max_towers, uint64_t* dst_d,
-                                uint32_t* shape_out, void* stream);
+int ofhe_dcrtpoly_upload_cereal(ofhe_ring* ring, const uint32_t* mod_idx_h, const void* buf_h, size_t len,
+                                uint32_t max_towers, int check_residues, uint64_t* dst_d, uint32_t* shape_out,
+                                void* stream);
 
 /* fills dst_d [n_limbs][N] with uniform residues in [0, q_l) from a counter-based generator (synthetic inputs) */
 int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const uint32_t* mod_idx_h, uint64_t seed,

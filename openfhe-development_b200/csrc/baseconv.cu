@@ -248,6 +248,54 @@ __global__ void __launch_bounds__(kThreads, OFHE_BCONV_MINB) bconv_kernel(RingDe
     }
 }
 
+// ---- more than 64 source limbs (the reference's depth-limit unit tests reach ~140: UnitTestBFVrnsCRTOperations.cpp:
+// 142-193).  Not a performance path: one thread per (coefficient, target limb), run-time loop over the sources, 64x64
+// products accumulated in 128 bits with a Barrett fold every 64 terms (64 * 2^120 < 2^127), the floating-point estimate
+// in the same index order as the fast kernel.  Same epilogues, same canonical results.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) bconv_wide_kernel(RingDev r, BConvDev t, LimbMap qmap, LimbMap pmap, PosMap xomap,
+                                                               const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                               size_t in_stride, size_t out_stride, int premultiplied) {
+    in += blockIdx.z * in_stride;
+    out += blockIdx.z * out_stride;
+    const uint32_t N = r.N, rr = blockIdx.x * kThreads + threadIdx.x, jj = blockIdx.y;
+    if (rr >= N)
+        return;
+    const ModConst mc = r.mc[pmap.idx[jj]];
+    const uint64_t p  = mc.q;
+    unsigned __int128 acc = 0;
+    double nu             = 0.5;
+    for (uint32_t i = 0; i < t.sizeQ; ++i) {
+        uint64_t y = in[(size_t)qmap.pos[i] * N + rr];
+        if (!premultiplied && MODE != 2)
+            y = shoup(y, t.qhatinv[2 * i], t.qhatinv[2 * i + 1], r.mc[qmap.idx[i]].q);
+        if (MODE != 0)
+            nu = __dadd_rn(nu, __dmul_rn(__ull2double_rn(y), t.dbl[i]));
+        const uint2 mm   = t.mat[(size_t)i * t.sizeP + jj];
+        const uint64_t m = (uint64_t)mm.x | ((uint64_t)mm.y << 30);
+        acc += (unsigned __int128)y * m;
+        if ((i & 63u) == 63u)
+            acc = barrett128((uint64_t)(acc >> 64), (uint64_t)acc, p, mc.mu128_hi, mc.mu128_lo);
+    }
+    uint64_t v = barrett128((uint64_t)(acc >> 64), (uint64_t)acc, p, mc.mu128_hi, mc.mu128_lo);
+    if (MODE == 1)
+        v = submod(v, t.alpha[(size_t)__double2ull_rz(nu) * t.sizeP + jj], p);
+    else if (MODE == 2) {
+        const uint64_t xo = in[(size_t)xomap.pos[jj] * N + rr];
+        v                 = addmod(v, mulmod(xo, t.extra[jj], mc), p);
+        uint64_t a;
+        if (fabs(nu) <= 9223372036854774784.0)
+            a = csub(lazy_reduce_n(__double2ull_rz(nu), mc.one_s, 0 - p), p);
+        else {
+            uint64_t hi, lo;
+            double_to_u128(nu, hi, lo);
+            a = barrett128(hi, lo, p, mc.mu128_hi, mc.mu128_lo);
+        }
+        v = addmod(v, a, p);
+    }
+    out[(size_t)pmap.pos[jj] * N + rr] = v;
+}
+
 }  // namespace
 
 BConv::~BConv() {
@@ -260,8 +308,19 @@ void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* o
                   size_t out_stride, bool premultiplied, cudaStream_t st) {
     if (t.sizeP == 0 || t.sizeQ == 0 || batch == 0)
         return;
-    OFHE_REQUIRE(t.sizeQ <= 64, "base conversion supports at most 64 source limbs");
     BConvDev d{t.sizeQ, t.sizeP, t.qhatinv_d, reinterpret_cast<const uint2*>(t.mat_d), t.mode, t.dbl_d, t.alpha_d, t.extra_d};
+    if (t.sizeQ > 64) {
+        dim3 g((r.N + kThreads - 1) / kThreads, t.sizeP, batch);
+        const int pmw = premultiplied ? 1 : 0;
+        if (t.mode == 0)
+            bconv_wide_kernel<0><<<g, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pmw);
+        else if (t.mode == 1)
+            bconv_wide_kernel<1><<<g, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pmw);
+        else
+            bconv_wide_kernel<2><<<g, kThreads, 0, st>>>(r.dev(), d, t.qmap, t.pmap, t.xomap, in, out, in_stride, out_stride, pmw);
+        OFHE_CUDA(cudaGetLastError());
+        return;
+    }
     static const int cpt1 = [] {
         const char* e = getenv("OFHE_BCONV_CPT");  // tuning knob: coefficients per thread for <= 16 source limbs
         return e ? atoi(e) : 1;

@@ -312,7 +312,7 @@ static void upload(void** dptr, const void* h, size_t bytes) {
 static std::unique_ptr<BConv> bconv_from_tables(const Ring& r, uint32_t n_src, const uint32_t* src, const uint32_t* src_pos,
                                                 const uint64_t* hatinv, uint32_t n_dst, const uint32_t* dst,
                                                 const uint64_t* mat_h, bool dst_major, uint32_t mat_cols) {
-    OFHE_REQUIRE(n_src >= 1 && n_src <= 64 && n_dst >= 1 && n_dst <= (uint32_t)kMaxLimbs, "base conversion: unsupported basis size");
+    OFHE_REQUIRE(n_src >= 1 && n_src <= (uint32_t)kMaxLimbs && n_dst >= 1 && n_dst <= (uint32_t)kMaxLimbs, "base conversion: unsupported basis size");
     std::vector<uint64_t> hinv(2 * (size_t)n_src);
     std::vector<uint32_t> mat(2 * (size_t)n_src * n_dst);
     for (uint32_t i = 0; i < n_src; ++i) {
@@ -872,15 +872,20 @@ __global__ void peer_barrier_kernel(PeerFlags pf, uint32_t world, uint32_t rank,
         uint64_t* theirs = pf.base[threadIdx.x] + row + rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
         const uint64_t* arrive = mine + threadIdx.x;
-        const long long t0     = clock64();
-        uint64_t seen          = 0;
+        uint64_t t0, now, seen = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
             if (seen >= epoch)
                 break;
-            if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz: give up rather than hang the device
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 10000000000ull) {  // 10 s of wall clock: a peer is gone
+                // count it, then abort the context: the phases behind this barrier would consume partially written
+                // gather buffers, so the failure must be LOUD (every later CUDA call of this rank returns an error)
+                // rather than a silently wrong ciphertext
                 atomicAdd(reinterpret_cast<unsigned long long*>(mine + world + 1), 1ULL);
-                break;
+                __threadfence_system();
+                __trap();
             }
             __nanosleep(64);
         }
@@ -1038,13 +1043,32 @@ int ofhe_cereal_dcrtpoly_write(uint32_t N, uint32_t n_towers, const uint64_t* mo
         std::memcpy(out_h, bytes.data(), bytes.size());
     });
 }
-int ofhe_dcrtpoly_upload_cereal(ofhe_ctx* ctx, const void* buf_h, size_t len, uint32_t max_towers, uint64_t* dst_d,
-                                uint32_t* shape_out, void* stream) {
+int ofhe_dcrtpoly_upload_cereal(ofhe_ring* ring, const uint32_t* mod_idx_h, const void* buf_h, size_t len,
+                                uint32_t max_towers, int check_residues, uint64_t* dst_d, uint32_t* shape_out,
+                                void* stream) {
     return guard([&] {
-        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        use(ring->r);
         std::vector<size_t> off;
-        const cio::DcrtInfo info = cio::scan_dcrtpoly(buf_h, len, nullptr, nullptr, &off);
+        std::vector<uint64_t> moduli;
+        const cio::DcrtInfo info = cio::scan_dcrtpoly(buf_h, len, &moduli, nullptr, &off);
+        // the archive is untrusted input: it must describe exactly the rows the caller sized dst_d for
+        OFHE_REQUIRE(info.N == ring->r->N, "serialized polynomial has a different ring dimension than the target ring");
         OFHE_REQUIRE(info.n_towers <= max_towers, "serialized polynomial has more towers than the destination slab");
+        for (uint32_t t = 0; t < info.n_towers; ++t) {
+            const uint32_t mi = mod_idx_h ? mod_idx_h[t] : t;
+            OFHE_REQUIRE(mi < ring->r->n_moduli, "modulus index out of range");
+            OFHE_REQUIRE(moduli[t] == ring->r->moduli[mi], "serialized tower modulus differs from the target ring's");
+            if (check_residues) {  // the kernels assume canonical residues (Barrett / 30-bit split bounds)
+                const uint64_t* w = reinterpret_cast<const uint64_t*>(static_cast<const uint8_t*>(buf_h) + off[t]);
+                uint64_t bad = 0;
+                for (uint32_t j = 0; j < info.N; ++j) {
+                    uint64_t v;
+                    std::memcpy(&v, w + j, 8);  // payload offsets are not 8-byte aligned in general
+                    bad |= (uint64_t)(v >= moduli[t]);
+                }
+                OFHE_REQUIRE(!bad, "serialized tower holds a residue >= its modulus");
+            }
+        }
         if (shape_out)
             shape_out[0] = info.N, shape_out[1] = info.n_towers, shape_out[2] = info.format;
         // every tower payload is N raw little-endian words: straight from the (ideally pinned) archive to its device row
@@ -1072,7 +1096,7 @@ int ofhe_fill_uniform(ofhe_ring* ring, uint64_t* dst_d, uint32_t n_limbs, const 
 namespace {
 std::unique_ptr<BConv> build_bconv(const Ring& r, uint32_t n_src, const uint32_t* src, uint32_t n_dst,
                                    const uint32_t* dst) {
-    OFHE_REQUIRE(n_src >= 1 && n_src <= 64 && n_dst >= 1 && n_dst <= (uint32_t)kMaxLimbs,
+    OFHE_REQUIRE(n_src >= 1 && n_src <= (uint32_t)kMaxLimbs && n_dst >= 1 && n_dst <= (uint32_t)kMaxLimbs,
                  "base conversion: unsupported basis size");
     std::vector<uint64_t> q(n_src);
     for (uint32_t i = 0; i < n_src; ++i)

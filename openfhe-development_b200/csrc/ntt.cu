@@ -59,6 +59,11 @@ struct NoHook {
 };
 // `after_first_barrier` runs right behind the first block barrier of the tile (the streaming kernels refill the
 // OTHER staging buffer there: every thread has then finished reading it)
+#if defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 3  // TIMING EXPERIMENT ONLY (wrong results): no block barriers in the forward rounds
+#define TILE_SYNC() __syncwarp()
+#else
+#define TILE_SYNC() __syncthreads()
+#endif
 template <int LOGN, typename Hook = NoHook>
 __device__ __forceinline__ void fwd_tile_rounds(uint64_t* sm, uint64_t (&x)[16], TwWin& w, const Twiddle* tw,
                                                 uint32_t tile, const Mod& m, uint32_t t,
@@ -71,7 +76,7 @@ __device__ __forceinline__ void fwd_tile_rounds(uint64_t* sm, uint64_t (&x)[16],
     for (int k = 0; k < 16; ++k)
         sm[t + 256 * k] = x[k];
     tw_preload<false>(w, tw, tb * 16u + bh);
-    __syncthreads();
+    TILE_SYNC();
     after_first_barrier();
     // ---- round B: tile bits 7..4, c = (t>>4)*256 + (t&15) + 16k
     prefetch_round(tw, tb * 256u + t);
@@ -79,12 +84,12 @@ __device__ __forceinline__ void fwd_tile_rounds(uint64_t* sm, uint64_t (&x)[16],
     for (int k = 0; k < 16; ++k)
         x[k] = sm[bh * 256 + bl + 16 * k];
     ct_round16_df<LOGN, S0 + 4>(x, w, tw, tb * 16u + bh, m);
-    __syncthreads();
+    TILE_SYNC();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
         sm[swz(bh * 256 + bl + 16 * k)] = x[k];
     tw_preload<false>(w, tw, tb * 256u + t);
-    __syncthreads();
+    TILE_SYNC();
     // ---- round C: tile bits 3..0, c = 16t + k (128 contiguous bytes per thread)
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -295,14 +300,27 @@ __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_tile(RingDev r, ui
     prefetch_round(tw, (1u << A) + tile);
 #pragma unroll
     for (int k = 0; k < 16; ++k)
+#if defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 5  // TIMING EXPERIMENT ONLY (wrong results): no global data load
+        x[k] = (uint64_t)(t + 256 * k) * 0x9E3779B97F4A7C15ull >> 5;
+#else
         x[k] = p[t + 256 * k];
+#endif
     TwWin ha;
     tw_preload<false>(ha, tw, (1u << A) + tile);
     fwd_tile_rounds<12 + A>(sm, x, ha, tw, tile, m, t);
     ulonglong2* d2 = reinterpret_cast<ulonglong2*>(p + 16 * t);
+#if defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 6  // TIMING EXPERIMENT ONLY (wrong results): one store instead of eight
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        acc ^= x[k];
+    if (acc == 0x1234567)
+        d2[0] = make_ulonglong2(acc, acc);
+#else
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         d2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
+#endif
 }
 template <int A>
 __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_tile(RingDev r, const uint64_t* in, uint64_t* out,
@@ -610,10 +628,14 @@ uint32_t stream_grid(const Ring& r, uint32_t n_items) {
     const uint32_t rounds = (n_items + cap - 1) / cap;
     return (n_items + rounds - 1) / rounds;
 }
-bool ntt_stream() {  // OFHE_NTT_STREAM=0 keeps the one-tile-per-CTA kernels (measurement switch)
+// OFHE_NTT_STREAM=1 selects the persistent TMA-fed tile kernels.  Measured on B200 (profiles/r02j_ntt_variants.txt):
+// bit-identical results, but 0.85 -> 1.02 us per forward limb-NTT at N = 2^16 -- the tile kernel is bound by the
+// latency of its per-thread twiddle loads, not by the tile load the copy engine hides, and the two staging buffers
+// cost L1 capacity (192 KiB of shared memory per SM leave 28 KiB of L1 for 180 KiB of twiddles in flight).  Default off.
+bool ntt_stream() {
     static const bool on = [] {
         const char* e = getenv("OFHE_NTT_STREAM");
-        return !e || e[0] != '0';
+        return e && e[0] == '1';
     }();
     return on;
 }

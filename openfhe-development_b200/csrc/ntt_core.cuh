@@ -232,6 +232,9 @@ __device__ __forceinline__ void ct_round(uint64_t* x, const Twiddle* __restrict_
 // twiddle load (profiles/r02h_tile_stalls.txt).  asm volatile keeps the loads in program order.
 __device__ __forceinline__ Twiddle ld_tw_pinned(const Twiddle* p) {
     Twiddle t;
+#if defined(OFHE_NTT_EXP) && OFHE_NTT_EXP == 4  // TIMING EXPERIMENT ONLY (wrong results): every twiddle from one cache line
+    p = reinterpret_cast<const Twiddle*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)0xFFFFF) + ((reinterpret_cast<uintptr_t>(p) >> 4) & 7);
+#endif
     asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(t.w), "=l"(t.ws) : "l"(p) : "memory");
     return t;
 }

@@ -622,6 +622,18 @@ B200T B200C B200C::ScaleAndRound(const std::shared_ptr<Params>& paramsOutput,
     const uint32_t sizeI  = sizeQP - sizeO;
     const bool outFirst =
         paramsOutput->GetParams()[0]->GetModulus() == m_h.GetParams()->GetParams()[0]->GetModulus();  // (:1528-1535)
+    if (sizeI == 0) {
+        // nothing is scaled away (the levelled BFV code calls this unconditionally, bfvrns-leveledshe.cpp:807): the
+        // reference's loop then reduces to x_j * tOSHatInvModsDivsModo[j][0] mod o_j with alpha = (uint64)0.5 = 0
+        std::vector<NativeInteger> s(sizeO);
+        for (uint32_t j = 0; j < sizeO; ++j)
+            s[j] = tOSHatInvModsDivsModo[j][0];
+        Host r = detail::TimesScalars(m_h, s, sizeO);
+        std::vector<PolyType> tw = std::move(r.GetAllElements());
+        for (uint32_t j = 0; j < sizeO; ++j)
+            ans.GetAllElements()[j].SetValues(tw[j].GetValues(), m_h.GetFormat());
+        return ans;
+    }
     detail::Op op(m_h.GetParams()->GetRingDimension());
     std::vector<uint64_t> mod, root;
     detail::Collect(towers, 0, sizeQP, mod, root);

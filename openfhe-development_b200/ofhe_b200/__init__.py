@@ -90,7 +90,7 @@ SIGNATURES = {
     "ofhe_cereal_dcrtpoly_scan": (C.c_int, [_vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_cereal_dcrtpoly_write": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp, C.c_size_t,
                                              C.POINTER(C.c_size_t)]),
-    "ofhe_dcrtpoly_upload_cereal": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_dcrtpoly_upload_cereal": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "ofhe_bfv_tables_host": (C.c_int, [C.c_uint32, _vp, C.c_uint32, _vp, C.c_uint64, C.c_int, _vp, C.POINTER(C.c_size_t)]),
     "ofhe_bfv_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "ofhe_bfv_destroy": (None, [_vp]),
@@ -224,18 +224,6 @@ class Context:
     def download(t):
         return t.detach().cpu().numpy().view(np.uint64)
 
-    def upload_cereal(self, buf, max_towers=256):
-        """Serialized DCRTPoly (the reference's portable-binary archive) -> ([n_towers][N] device slab, scan info).
-        Pass a pinned buffer (e.g. a torch uint8 tensor from pin_memory()) for truly asynchronous copies."""
-        import torch
-
-        info = cereal_scan_dcrtpoly(buf if not hasattr(buf, "numpy") else buf.numpy(), max_towers)
-        dst = self.zeros(info["n_towers"], info["N"])
-        b = buf.numpy() if hasattr(buf, "numpy") else np.frombuffer(buf, dtype=np.uint8)
-        _ck(lib().ofhe_dcrtpoly_upload_cereal(self.h, b.ctypes.data, b.size, max_towers, _ptr(dst), None, _stream()))
-        torch.cuda.current_stream().synchronize()  # `b` may be a temporary view of the caller's bytes
-        return dst, info
-
     # raw cudaMalloc buffers (zero-filled) for the peer-push exchange: IPC handles exist only for whole allocations
     def raw_zeros(self, words):
         p = _vp()
@@ -301,6 +289,22 @@ class Ring:
         _ck(lib().ofhe_ring_twiddles_host(self.h, mod_idx, T.ctypes.data, Tp.ctypes.data, Ti.ctypes.data,
                                           Tip.ctypes.data, C.byref(ni), C.byref(nip)))
         return T, Tp, Ti, Tip, ni.value, nip.value
+
+    def upload_cereal(self, buf, mod_idx=None, check_residues=True):
+        """Serialized DCRTPoly (the reference's portable-binary archive) -> [n_towers][N] device slab of THIS ring.
+        The archive is rejected unless its ring dimension and tower moduli match the ring's (mod_idx: ring index of
+        every tower, default 0..n-1).  Pass a pinned uint8 torch tensor for truly asynchronous copies."""
+        import torch
+
+        b = buf.numpy() if hasattr(buf, "numpy") else np.frombuffer(buf, dtype=np.uint8)
+        n = len(self.moduli) if mod_idx is None else len(mod_idx)
+        dst = self.ctx.zeros(n, self.N)
+        shape = (C.c_uint32 * 3)()
+        mi = None if mod_idx is None else _idx(mod_idx)
+        _ck(lib().ofhe_dcrtpoly_upload_cereal(self.h, None if mi is None else mi.ctypes.data, b.ctypes.data, b.size, n,
+                                              1 if check_residues else 0, _ptr(dst), shape, _stream()))
+        torch.cuda.current_stream().synchronize()  # `b` may be a temporary view of the caller's bytes
+        return dst[: shape[1]], {"N": shape[0], "n_towers": shape[1], "format": shape[2]}
 
     # DCRTPoly::SwitchFormat pieces
     def ntt_fwd(self, src, dst, mod_idx):

@@ -197,6 +197,21 @@ def test_approx_switch_crt_basis_vs_oracle(gpu, oracle):
         ring.close()
     finally:
         c.close()
+    # more than 64 source limbs (the reference's depth-limit tests reach ~140): the run-time-loop kernel
+    c = oracle.ckks(1 << 8, 79, 50, 60, 1, 0)  # one digit of 80 limbs -> 27 aux primes
+    try:
+        N = 1 << 8
+        ring = _ring(gpu, N, c.moduli, c.roots)
+        x = seeded_residues(11, c.moduli[:c.sizeQ], N)
+        x[:, 0] = c.moduli[:c.sizeQ] - np.uint64(1)
+        hatmod, compl = c.PartQlHatModp(c.sizeQ, 0)
+        want = oracle.approx_switch_crt_basis(c.moduli[:c.sizeQ], c.PartQlHatInvModq(0, c.sizeQ), compl, hatmod, x)
+        o = ctx.zeros(c.sizeQP - c.sizeQ, N)
+        ring.approx_switch_crt_basis(list(range(c.sizeQ)), list(range(c.sizeQ, c.sizeQP)), ctx.upload(x), o)
+        assert (ctx.download(o) == want).all()
+        ring.close()
+    finally:
+        c.close()
 
 
 def _hks_from_golden(gpu, g):
@@ -499,3 +514,42 @@ def test_config4_shape_n17(gpu, oracle):
             o.close()
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+def test_upload_cereal_archive(gpu):
+    """f3: archive bytes of the reference's wire format -> device rows of a ring (ofhe_dcrtpoly_upload_cereal); the
+    archive is untrusted: wrong ring dimension, wrong modulus, too many towers or a non-canonical residue are rejected"""
+    ctx, m = gpu
+    N, L = 1 << 12, 5
+    q, roots = m.dcrt_params(N, L, 60)
+    data = seeded_residues(31, q, N)
+    blob = m.cereal_write_dcrtpoly(q, roots, 0, data)  # byte-identical to Serial::Serialize (tests/test_cereal_io.py)
+    ring = m.Ring(ctx, N, q, roots)
+    slab, info = ring.upload_cereal(blob)
+    assert (info["N"], info["n_towers"], info["format"]) == (N, L, 0)
+    assert (ctx.download(slab) == data).all()
+    # the uploaded rows are usable as they are: NTT round trip on the device
+    tmp = ctx.zeros(L, N)
+    ring.ntt_inv(slab, tmp, list(range(L)))
+    ring.ntt_fwd(tmp, tmp, list(range(L)))
+    assert (ctx.download(tmp) == data).all()
+    # towers in another order of the ring
+    perm = [4, 0, 3, 1, 2]
+    slab2, _ = m.Ring(ctx, N, q[perm], roots[perm]).upload_cereal(m.cereal_write_dcrtpoly(q, roots, 0, data),
+                                                                     mod_idx=[perm.index(i) for i in range(L)])
+    assert (ctx.download(slab2) == data).all()
+    # rejections
+    q2, r2 = m.dcrt_params(2 * N, L, 60)
+    with pytest.raises(RuntimeError, match="ring dimension"):
+        ring.upload_cereal(m.cereal_write_dcrtpoly(q2, r2, 0, seeded_residues(32, q2, 2 * N)))
+    with pytest.raises(RuntimeError, match="modulus differs"):
+        ring.upload_cereal(m.cereal_write_dcrtpoly(q[::-1].copy(), roots[::-1].copy(), 0, data[::-1].copy()))
+    with pytest.raises(RuntimeError, match="more towers"):
+        m.Ring(ctx, N, q[:3], roots[:3]).upload_cereal(blob)
+    bad = data.copy()
+    bad[2, 17] = q[2]
+    with pytest.raises(RuntimeError, match="residue"):
+        ring.upload_cereal(m.cereal_write_dcrtpoly(q, roots, 0, bad))
+    slab3, _ = ring.upload_cereal(m.cereal_write_dcrtpoly(q, roots, 0, bad), check_residues=False)
+    assert (ctx.download(slab3) == bad).all()

@@ -16,4 +16,4 @@ run bgv pke_tests_b200 '*UTBGVRNS.*' 400
 run bfv pke_tests_b200 '*UTBFVRNS.*' 400
 run ckksauto pke_tests_b200 '*UTCKKSRNS_AUTOMORPHISM*' 300
 run she pke_tests_b200 '*UTGENERAL_SHE*' 400
-run boot pke_tests_b200 '*UTCKKSRNS_BOOT*FULL_0*' 600
+run boot pke_tests_b200 "*UTCKKSRNS_BOOT*" 900
