@@ -330,6 +330,10 @@ class Ring:
     def automorphism(self, dst, src, n_limbs, k):
         _ck(lib().ofhe_automorphism(self.h, _ptr(dst), _ptr(src), n_limbs, k, _stream()))
 
+    def automorphism_coeff(self, dst, src, mod_idx, k):
+        mi = _idx(mod_idx)
+        _ck(lib().ofhe_automorphism_coeff(self.h, _ptr(dst), _ptr(src), len(mi), mi.ctypes.data, k, _stream()))
+
     def automorphism_map(self, k):
         m = np.empty(self.N, dtype=np.uint32)
         _ck(lib().ofhe_automorphism_map_host(self.h, k, m.ctypes.data))

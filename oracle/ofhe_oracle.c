@@ -359,6 +359,13 @@ void orc_automorphism_eval(uint32_t N, const uint32_t* map, const uint64_t* in, 
     for (uint32_t j = 0; j < N; ++j)
         out[j] = in[map[j]];
 }
+/* COEFFICIENT format, poly-impl.h:359-362: out[jk mod N] = ((jk div N) odd) ? q - in[j] : in[j]; the subtraction is a
+ * plain integer one, so a zero coefficient with an odd wrap count comes out as q (not reduced), as in the reference. */
+void orc_automorphism_coeff(uint32_t N, uint32_t k, uint64_t q, const uint64_t* in, uint64_t* out) {
+    uint32_t logn = ilog2(N), mask = N - 1;
+    for (uint32_t j = 0, jk = 0; j < N; ++j, jk += k)
+        out[jk & mask] = ((jk >> logn) & 1u) ? q - in[j] : in[j];
+}
 
 /* ------------------------------------------------------------------ a10: ApproxSwitchCRTBasis
  * dcrtpoly-impl.h:888-918 (int128 branch): y_i = x_i * QHatInv_i mod q_i (Shoup);

@@ -45,6 +45,7 @@ void orc_limb_mul_scalar(uint64_t q, uint32_t N, const uint64_t* a, uint64_t s, 
 void orc_switch_modulus(uint32_t N, uint64_t q_from, uint64_t q_to, uint64_t* x);
 void orc_automorphism_map(uint32_t N, uint32_t k, uint32_t* map);
 void orc_automorphism_eval(uint32_t N, const uint32_t* map, const uint64_t* in, uint64_t* out);
+void orc_automorphism_coeff(uint32_t N, uint32_t k, uint64_t q, const uint64_t* in, uint64_t* out);
 
 /* a10 fast base conversion: in [sizeQ][N] COEFF -> out [sizeP][N] COEFF; QHatModp is [sizeQ][sizeP] */
 void orc_approx_switch_crt_basis(uint32_t N, uint32_t sizeQ, const uint64_t* q, const uint64_t* QHatInvModq,

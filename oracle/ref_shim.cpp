@@ -289,6 +289,15 @@ int ref_dcrt_automorphism(uint32_t N, uint32_t L, const uint64_t* moduli, const 
         dump_poly(A.AutomorphismTransform(k, vec), out);
     });
 }
+// COEFFICIENT-format automorphism: DCRTPolyImpl::AutomorphismTransform(k) -> PolyImpl::AutomorphismTransform(k)
+int ref_dcrt_automorphism_coeff(uint32_t N, uint32_t L, const uint64_t* moduli, const uint64_t* roots, uint32_t k,
+                                const uint64_t* a, uint64_t* out) {
+    return guarded([&] {
+        auto params = make_params(N, L, moduli, roots);
+        DCRTPoly A  = make_poly(params, Format::COEFFICIENT, a);
+        dump_poly(A.AutomorphismTransform(k), out);
+    });
+}
 int ref_automorphism_map(uint32_t N, uint32_t k, uint32_t* map) {
     return guarded([&] {
         std::vector<uint32_t> vec(N);

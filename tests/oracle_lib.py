@@ -86,6 +86,7 @@ class Oracle:
         _sig(L, "orc_switch_modulus", None, C.c_uint32, C.c_uint64, C.c_uint64, u64p)
         _sig(L, "orc_automorphism_map", None, C.c_uint32, C.c_uint32, u32p)
         _sig(L, "orc_automorphism_eval", None, C.c_uint32, u32p, u64p, u64p)
+        _sig(L, "orc_automorphism_coeff", None, C.c_uint32, C.c_uint32, C.c_uint64, u64p, u64p)
         _sig(L, "orc_approx_switch_crt_basis", None, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p,
              u64p, u64p)
         _sig(L, "orc_switch_crt_basis", None, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p, u64p, f64p,
@@ -171,6 +172,13 @@ class Oracle:
     def dcrt_automorphism(self, k, a):
         m = self.automorphism_map(a.shape[1], k)
         return np.ascontiguousarray(a[:, m])
+
+    def dcrt_automorphism_coeff(self, q, k, a):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        for i in range(a.shape[0]):
+            self.L.orc_automorphism_coeff(a.shape[1], k, int(q[i]), a[i], out[i])
+        return out
 
     def approx_switch_crt_basis(self, q, QHatInvModq, p, QHatModp, x):
         q, p = np.ascontiguousarray(q, dtype=np.uint64), np.ascontiguousarray(p, dtype=np.uint64)
@@ -375,6 +383,7 @@ class Reference:
         _sig(L, "ref_dcrt_serialize", C.c_size_t, C.c_uint32, C.c_uint32, u64p, u64p, C.c_int, u64p, C.c_int,
              C.c_void_p, C.c_size_t)
         _sig(L, "ref_dcrt_automorphism", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p)
+        _sig(L, "ref_dcrt_automorphism_coeff", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p)
         _sig(L, "ref_automorphism_map", C.c_int, C.c_uint32, C.c_uint32, u32p)
         _sig(L, "ref_switch_modulus", C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, u64p)
         _sig(L, "ref_time_switch_format", C.c_double, C.c_uint32, C.c_uint32, u64p, u64p, u64p, C.c_int)
@@ -474,6 +483,12 @@ class Reference:
         out = np.empty_like(a)
         self._ok(self.L.ref_dcrt_automorphism(a.shape[1], a.shape[0], np.ascontiguousarray(moduli),
                                               np.ascontiguousarray(roots), k, np.ascontiguousarray(a), out))
+        return out
+
+    def dcrt_automorphism_coeff(self, moduli, roots, k, a):
+        out = np.empty_like(a)
+        self._ok(self.L.ref_dcrt_automorphism_coeff(a.shape[1], a.shape[0], np.ascontiguousarray(moduli),
+                                                    np.ascontiguousarray(roots), k, np.ascontiguousarray(a), out))
         return out
 
     def automorphism_map(self, N, k):

@@ -127,6 +127,11 @@ def test_limb_ops_golden_and_oracle(gpu, oracle, golden):
         ring.automorphism(out, a, 2, k)
         assert (ctx.download(out) == g[f"n64_auto{k}"]).all()
         assert (ring.automorphism_map(k) == oracle.automorphism_map(64, k)).all()
+        # COEFFICIENT-format branch (a15, poly-impl.h:359-362): a zero coefficient with an odd wrap count becomes q
+        az = g["n64_a"].copy()
+        az[:, :3] = 0
+        ring.automorphism_coeff(out, ctx.upload(az), [0, 1], k)
+        assert (ctx.download(out) == oracle.dcrt_automorphism_coeff(q, k, az)).all()
     o1 = ctx.zeros(1, 64)
     ring.switch_modulus(o1, a[0:1], 0, 1)
     assert (ctx.download(o1)[0] == g["n64_swmod_down"]).all()

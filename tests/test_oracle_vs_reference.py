@@ -62,6 +62,8 @@ def test_limb_ops(oracle, reference):
     for k in (3, 5, 25, 2 * N - 1):
         assert (oracle.automorphism_map(N, k) == reference.automorphism_map(N, k)).all()
         assert (oracle.dcrt_automorphism(k, a) == reference.dcrt_automorphism(q, roots, k, a)).all()
+        # COEFFICIENT-format branch (poly-impl.h:359-362), including the zero coefficient that comes out as q
+        assert (oracle.dcrt_automorphism_coeff(q, k, a) == reference.dcrt_automorphism_coeff(q, roots, k, a)).all()
     for f, t in [(0, 1), (1, 0), (0, 2), (2, 0)]:
         assert (oracle.switch_modulus(q[f], q[t], a[f]) == reference.switch_modulus(q[f], q[t], a[f])).all()
 

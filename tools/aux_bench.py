@@ -149,10 +149,69 @@ def config5(m, torch, ctx):
                         "where 256 limbs allow", "peak_gbs": peak, "rows": rows}
 
 
+def config2_resident(m, torch, ctx):
+    """SURVEY 8 f1/f2 at the SIZE of BASELINE config 2 (N = 2^16, 45 + 15 limbs, dnum 3): device-resident chains and
+    hoisted rotations, eager and as one CUDA graph.  Synthetic residues and keys (throughput does not depend on them);
+    the same entry points are parity-tested bit-exact at N = 4096 (tests/test_gpu_chain.py, test_gpu_parity.py)."""
+    p = m.ckks_paramgen(1 << 16, 44, 59, 60, 3, 0)
+    N, L, sizeP = p["N"], p["sizeQ"], p["sizeP"]
+    ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+    hks = m.Hks(ring, L, sizeP, p["dnum"])
+    evk, rk = m.EvalKey(hks, seed=11), m.EvalKey(hks, seed=12)
+    ct1, ct2 = ctx.zeros(2, L, N), ctx.zeros(2, L, N)
+    ring.fill_uniform(ct1.view(2 * L, N), list(range(L)) * 2, 21)
+    ring.fill_uniform(ct2.view(2 * L, N), list(range(L)) * 2, 22)
+    b_m, b_r = ctx.zeros(2, L, N), ctx.zeros(2, L - 1, N)
+    b_rot, b_s = ctx.zeros(2, L - 1, N), ctx.zeros(2, L - 1, N)
+    k = m.find_automorphism_index(1, 2 * N)
+    idx2 = list(range(L - 1)) * 2
+    for lvl in (L, L - 1):
+        hks.reserve(lvl)
+
+    def chain():  # EvalMult -> Rescale -> EvalRotate -> EvalAdd, nothing leaves the device
+        hks.evalmult(L, ct1, ct2, evk, b_m)
+        hks.rescale(L, b_m, b_r, 2)
+        hks.rotate(L - 1, k, b_r, rk, b_rot)
+        ring.binop(0, b_s.view(2 * (L - 1), N), b_rot.view(2 * (L - 1), N), b_r.view(2 * (L - 1), N), idx2)
+
+    out = {"workload": "CKKS chain EvalMult+relin -> Rescale -> EvalRotate (own key) -> EvalAdd, N=2^16, 45+15 limbs, "
+                       "device-resident (SURVEY 8 f1)"}
+    out["chain_us_eager"] = _timeit(torch, chain, 10)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        chain()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            chain()
+        out["chain_us_graph"] = _timeit(torch, g.replay, 10)
+    out["rescale_us"] = _timeit(torch, lambda: hks.rescale(L, b_m, b_r, 2), 20)
+    out["rotate_us"] = _timeit(torch, lambda: hks.rotate(L - 1, k, b_r, rk, b_rot), 20)
+    out["rotations_per_s"] = 1e6 / out["rotate_us"]
+    # hoisted rotations (SURVEY 8 f2): one ModUp shared by R rotations of the same ciphertext
+    R = 8
+    nd = hks.num_digits(L - 1)
+    digits = ctx.zeros(nd, L - 1 + sizeP, N)
+    outs = [ctx.zeros(2, L - 1, N) for _ in range(2)]
+
+    def hoisted():
+        hks.modup(L - 1, b_r[1], digits)
+        for j in range(R):
+            hks.fast_rotation(L - 1, k, b_r, digits, rk, outs[j & 1])
+
+    us = _timeit(torch, hoisted, 5)
+    out["hoisted_8_rotations_us"] = us
+    out["hoisted_rotations_per_s"] = R * 1e6 / us
+    for o in (evk, rk, hks, ring):
+        o.close()
+    return out
+
+
 def run(m, torch, ctx):
     out = {}
-    for name, fn in (("config1_ntt4096_single_limb", config1), ("config3_bfv_evalmult_n15", config3),
-                     ("config5_ntt_sweep", config5)):
+    for name, fn in (("config1_ntt4096_single_limb", config1), ("config2_resident_chain_and_rotations", config2_resident),
+                     ("config3_bfv_evalmult_n15", config3), ("config5_ntt_sweep", config5)):
         try:
             out[name] = fn(m, torch, ctx)
         except Exception as ex:
