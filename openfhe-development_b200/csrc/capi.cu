@@ -307,7 +307,7 @@ int ofhe_approx_switch_crt_basis(ofhe_ring* ring, uint32_t n_src, const uint32_t
 
 static void upload(void** dptr, const void* h, size_t bytes) {
     OFHE_CUDA(cudaMalloc(dptr, bytes));
-    OFHE_CUDA(cudaMemcpy(*dptr, h, bytes, cudaMemcpyHostToDevice));
+    h2d_blocking(*dptr, h, bytes);
 }
 static std::unique_ptr<BConv> bconv_from_tables(const Ring& r, uint32_t n_src, const uint32_t* src, const uint32_t* src_pos,
                                                 const uint64_t* hatinv, uint32_t n_dst, const uint32_t* dst,
@@ -498,8 +498,8 @@ int ofhe_evk_create(ofhe_hks* hks, const uint64_t* a_h, const uint64_t* b_h, ofh
         k->dnum      = h.dnum;
         OFHE_CUDA(cudaMalloc(&k->a_d, words * sizeof(uint64_t)));
         OFHE_CUDA(cudaMalloc(&k->b_d, words * sizeof(uint64_t)));
-        OFHE_CUDA(cudaMemcpy(k->a_d, a_h, words * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        OFHE_CUDA(cudaMemcpy(k->b_d, b_h, words * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        h2d_blocking(k->a_d, a_h, words * sizeof(uint64_t));
+        h2d_blocking(k->b_d, b_h, words * sizeof(uint64_t));
         *out = new ofhe_evk{k.release()};
     });
 }
@@ -1120,8 +1120,8 @@ std::unique_ptr<BConv> build_bconv(const Ring& r, uint32_t n_src, const uint32_t
     t->pmap  = make_map(dst, n_dst);
     OFHE_CUDA(cudaMalloc(&t->qhatinv_d, sizeof(uint64_t) * hinv.size()));
     OFHE_CUDA(cudaMalloc(&t->mat_d, sizeof(uint32_t) * mat.size()));
-    OFHE_CUDA(cudaMemcpy(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size(), cudaMemcpyHostToDevice));
-    OFHE_CUDA(cudaMemcpy(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size(), cudaMemcpyHostToDevice));
+    h2d_blocking(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size());
+    h2d_blocking(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size());
     return t;
 }
 }  // namespace

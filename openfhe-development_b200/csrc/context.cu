@@ -113,9 +113,9 @@ Ring* ring_create(Context* ctx, uint32_t N, uint32_t n_moduli, const uint64_t* m
         OFHE_CUDA(cudaMalloc(&r->mc_d, sizeof(ModConst) * n_moduli));
         OFHE_CUDA(cudaMalloc(&r->tw_fwd_d, sizeof(Twiddle) * fwd.size()));
         OFHE_CUDA(cudaMalloc(&r->tw_inv_d, sizeof(Twiddle) * inv.size()));
-        OFHE_CUDA(cudaMemcpy(r->mc_d, r->mc_h.data(), sizeof(ModConst) * n_moduli, cudaMemcpyHostToDevice));
-        OFHE_CUDA(cudaMemcpy(r->tw_fwd_d, fwd.data(), sizeof(Twiddle) * fwd.size(), cudaMemcpyHostToDevice));
-        OFHE_CUDA(cudaMemcpy(r->tw_inv_d, inv.data(), sizeof(Twiddle) * inv.size(), cudaMemcpyHostToDevice));
+        h2d_blocking(r->mc_d, r->mc_h.data(), sizeof(ModConst) * n_moduli);
+        h2d_blocking(r->tw_fwd_d, fwd.data(), sizeof(Twiddle) * fwd.size());
+        h2d_blocking(r->tw_inv_d, inv.data(), sizeof(Twiddle) * inv.size());
     }
     catch (...) {
         delete r;

@@ -58,8 +58,8 @@ std::unique_ptr<BConv> make_bconv(const Ring& r, const std::vector<uint32_t>& sr
     }
     OFHE_CUDA(cudaMalloc(&t->qhatinv_d, sizeof(uint64_t) * hinv.size()));
     OFHE_CUDA(cudaMalloc(&t->mat_d, sizeof(uint32_t) * mat.size()));
-    OFHE_CUDA(cudaMemcpy(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size(), cudaMemcpyHostToDevice));
-    OFHE_CUDA(cudaMemcpy(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size(), cudaMemcpyHostToDevice));
+    h2d_blocking(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size());
+    h2d_blocking(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size());
     return t;
 }
 
@@ -155,7 +155,7 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
             }
         }
         OFHE_CUDA(cudaMalloc(&lv->fold_modup_d, sizeof(uint64_t) * fold.size()));
-        OFHE_CUDA(cudaMemcpy(lv->fold_modup_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
+        h2d_blocking(lv->fold_modup_d, fold.data(), sizeof(uint64_t) * fold.size());
     }
     if (sizeP) {
         const uint64_t* P = r.moduli.data() + sizeQ;
@@ -166,7 +166,7 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
                 make_inv_fold(r, sizeQ + j, w, &fold[4 * (size_t)(2 * j + b)]);
             }
         OFHE_CUDA(cudaMalloc(&lv->fold_moddown_d, sizeof(uint64_t) * fold.size()));
-        OFHE_CUDA(cudaMemcpy(lv->fold_moddown_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
+        h2d_blocking(lv->fold_moddown_d, fold.data(), sizeof(uint64_t) * fold.size());
     }
     // ---- ModDown: P rows -> Ql rows  (PHatInvModp / PHatModq, rns-cryptoparameters.cpp:214-229)
     if (sizeP) {

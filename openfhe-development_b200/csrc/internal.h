@@ -61,6 +61,16 @@ struct Error : std::runtime_error {
             throw ::ofhe::Error(msg);      \
     } while (0)
 
+// Blocking host-to-device copy for one-time table / key uploads.  cudaMemcpy from PAGEABLE memory returns once the source
+// is staged, possibly before the DMA into device memory has finished, and only the legacy default stream is ordered
+// behind it; callers of this library launch on their own NON-BLOCKING streams (one per host thread in the lattice
+// backend), which are not.  The explicit wait on the legacy stream closes that window (round 2: intermittently wrong
+// first use of a freshly uploaded evaluation key under the relinked reference's test suites).
+inline void h2d_blocking(void* dst, const void* src, size_t bytes) {
+    OFHE_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    OFHE_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+}
+
 struct Context {
     int device = 0;
     int sm_count = 0;

@@ -106,7 +106,7 @@ Shard::Level& Shard::level(uint32_t sizeQl) {
             lv->gatherq_pos.pos[t] = (uint16_t)(rank * lv->slotsQ + t);
         }
         OFHE_CUDA(cudaMalloc(&lv->fold_q_d, sizeof(uint64_t) * fold.size()));
-        OFHE_CUDA(cudaMemcpy(lv->fold_q_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
+        h2d_blocking(lv->fold_q_d, fold.data(), sizeof(uint64_t) * fold.size());
     }
     // phase B: per digit, convert the gathered digit limbs into the OWNED complementary rows of that digit's local slab
     lv->map_modup_ntt.n = 0;
@@ -153,7 +153,7 @@ Shard::Level& Shard::level(uint32_t sizeQl) {
                 lv->gatherp_pos.pos[n] = (uint16_t)((rank * 2 + b) * slotsP + t);
             }
         OFHE_CUDA(cudaMalloc(&lv->fold_p_d, sizeof(uint64_t) * fold.size()));
-        OFHE_CUDA(cudaMemcpy(lv->fold_p_d, fold.data(), sizeof(uint64_t) * fold.size(), cudaMemcpyHostToDevice));
+        h2d_blocking(lv->fold_p_d, fold.data(), sizeof(uint64_t) * fold.size());
     }
     // phase C: all P limbs (gathered) -> the owned Q rows, both polynomials in one launch
     if (nq) {

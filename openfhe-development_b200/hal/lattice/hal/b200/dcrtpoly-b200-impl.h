@@ -200,6 +200,8 @@ inline void Binop(int opc, const Host& a, const Host* b, Host& dst) {
     uint64_t* db    = da;
     op.Up(da, ta, 0, L);
     if (b) {
+        if (b->GetAllElements().size() < L)
+            OPENFHE_THROW("b200 backend: right-hand side has fewer towers than the left-hand side");
         db = op.Slab(1, L);
         op.Up(db, b->GetAllElements(), 0, L);
     }
@@ -211,18 +213,19 @@ inline void Binop(int opc, const Host& a, const Host* b, Host& dst) {
 }
 }  // namespace detail
 
+// The Eq forms perform NO checks in the reference (:374-380, :402-408, dcrtpoly.h:117-123): they combine this
+// polynomial's towers with the FIRST as many towers of rhs, and callers rely on that (rhs with more towers:
+// FHECKKSRNS::KeySwitchSparse, ckksrns-fhe.cpp:3650).  A shorter rhs is undefined behaviour there and an error here.
 B200T B200C& B200C::operator+=(const DCRTPolyType& rhs) {
-    detail::CheckPair(m_h, rhs.m_h, false);
     detail::Binop(0, m_h, &rhs.m_h, m_h);
     return *this;
 }
 B200T B200C& B200C::operator-=(const DCRTPolyType& rhs) {
-    detail::CheckPair(m_h, rhs.m_h, false);
     detail::Binop(1, m_h, &rhs.m_h, m_h);
     return *this;
 }
 B200T B200C& B200C::operator*=(const DCRTPolyType& rhs) {
-    detail::Binop(2, m_h, &rhs.m_h, m_h);  // the reference's operator*= performs no checks (dcrtpoly.h:117-123)
+    detail::Binop(2, m_h, &rhs.m_h, m_h);
     return *this;
 }
 B200T B200C B200C::Plus(const DCRTPolyType& rhs) const {

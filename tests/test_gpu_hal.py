@@ -70,4 +70,21 @@ def test_bfvrns():
 def test_ckksrns_bootstrap():
     """UTCKKSRNS_BOOT (UnitTestBootstrap.cpp): EvalBootstrap = ModRaise + CoeffsToSlots / SlotsToCoeffs BSGS linear
     transforms over hoisted rotations + EvalChebyshev, all through the backend (BASELINE config 4's code path)"""
-    run_suite("pke_tests_b200", "*UTCKKSRNS_BOOT*BOOTSTRAP_FULL_0*", 1500, ["limb_ntt", "modup", "moddown", "automorph_limbs"])
+    run_suite("pke_tests_b200", "*UTCKKSRNS_BOOT*", 1800, ["limb_ntt", "modup", "moddown", "automorph_limbs"])
+
+
+def test_ckksrns_serialization():
+    """UTCKKSRNS_SER (UnitTestCKKSrnsSerialize.cpp): contexts, keys and ciphertexts written and read back through the
+    backend class's save/load (same three fields, same order as dcrtpoly.h:337-351), then used on the device path"""
+    run_suite("pke_tests_b200", "*UTCKKSRNS_SER*", 900, ["limb_ntt"])
+
+
+def test_general_she():
+    """UTGENERAL_SHE (UnitTestSHE.cpp): EvalAdd/Sub/Mult/Square/Sum/Merge/AtIndex over BFV (all four multiplication
+    techniques), BGV and CKKS"""
+    run_suite("pke_tests_b200", "*UTGENERAL_SHE*", 900, ["limb_ntt", "ew_limbs", "bconv"])
+
+
+def test_ckksrns_automorphism():
+    """UTCKKSRNS_AUTOMORPHISM (UnitTestCKKSrnsAutomorphism.cpp)"""
+    run_suite("pke_tests_b200", "*UTCKKSRNS_AUTOMORPHISM*", 600, ["limb_ntt", "automorph_limbs", "moddown"])
