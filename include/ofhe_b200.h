@@ -212,6 +212,24 @@ int ofhe_ckks_fast_rotation_ext(ofhe_hks* hks, uint32_t sizeQl, uint32_t k, int 
 int ofhe_hks_keyswitch_ext(ofhe_hks* hks, uint32_t sizeQl, int add_first, const uint64_t* ct_d, uint64_t* out_ext_d,
                            void* stream);
 
+/* ---- f2  one level of the double-hoisted baby-step / giant-step linear transform: the body of the `for s` loops of
+ *      FHECKKSRNS::EvalCoeffsToSlots / EvalSlotsToCoeffs   pke/lib/scheme/ckksrns/ckksrns-fhe.cpp:1934-1987, 2094-2139
+ *      (EvalLinearTransform :1834-1882 is the same scheme with one hoisting level), every intermediate device resident:
+ *        digits = EvalFastRotationPrecompute(ct);  fr[j] = EvalFastRotationExt(ct, k_in[j], digits, true) | KeySwitchExt(ct, true)
+ *        for i < b: inner = sum_j fr[j] (.) A[g i + j]  (EvalMultExt / EvalAddExtInPlace; g i + j == skip left out, j > 0)
+ *                   first (+)= KeySwitchDown(inner)_0 [rotated by k_out[i]];  outer (+)= EvalFastRotationExt(KeySwitchDown(inner), k_out[i]) | inner
+ *        out = KeySwitchDown(outer); out_0 += first
+ *      k_in_h[g] / k_out_h[b]: AUTOMORPHISM indices (ofhe_find_automorphism_index of the rotation; 0 = no rotation) with
+ *      their keys; k_out_h[0] is ignored (the reference's i == 0 branch never rotates).  A_d [b*g][sizeQl+sizeP][N]: the
+ *      pre-encoded diagonals in the extended basis QlP (EVALUATION).  ct_d, out_d [2][sizeQl][N].  ws_d: caller-owned
+ *      workspace of ofhe_ckks_bsgs_workspace_words(hks, sizeQl, g) words -- the call allocates nothing, is asynchronous
+ *      on `stream` and capturable once ofhe_hks_reserve(hks, sizeQl, stream) has run.                                   */
+size_t ofhe_ckks_bsgs_workspace_words(const ofhe_hks* hks, uint32_t sizeQl, uint32_t g);
+int ofhe_ckks_bsgs_level(ofhe_hks* hks, uint32_t sizeQl, uint32_t g, uint32_t b, const uint32_t* k_in_h,
+                         const uint32_t* k_out_h, const ofhe_evk* const* evk_in_h, const ofhe_evk* const* evk_out_h,
+                         const uint64_t* A_d, uint32_t skip, const uint64_t* ct_d, uint64_t* out_d, uint64_t* ws_d,
+                         void* stream);
+
 /* ---- a20 (host helper, setup time) CKKS modulus chain + auxiliary primes with the reference's selection rules
  *      ParameterGenerationCKKSRNS::SinglePrimeModuliGen  pke/lib/scheme/ckksrns/ckksrns-parametergeneration.cpp:409-518
  *      scal_tech: 0 FIXEDMANUAL 1 FIXEDAUTO 2 FLEXIBLEAUTO 3 FLEXIBLEAUTOEXT (sizeQ = depth + 2).  shape_out: sizeQ, sizeP, dnum, alpha.

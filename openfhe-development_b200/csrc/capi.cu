@@ -728,6 +728,32 @@ int ofhe_hks_keyswitch_ext(ofhe_hks* hks, uint32_t sizeQl, int add_first, const 
         hks->h->keyswitch_ext(sizeQl, add_first != 0, ct_d, out_ext_d, S(stream));
     });
 }
+size_t ofhe_ckks_bsgs_workspace_words(const ofhe_hks* hks, uint32_t sizeQl, uint32_t g) {
+    return hks->h->bsgs_workspace_words(sizeQl, g);
+}
+int ofhe_ckks_bsgs_level(ofhe_hks* hks, uint32_t sizeQl, uint32_t g, uint32_t b, const uint32_t* k_in_h,
+                         const uint32_t* k_out_h, const ofhe_evk* const* evk_in_h, const ofhe_evk* const* evk_out_h,
+                         const uint64_t* A_d, uint32_t skip, const uint64_t* ct_d, uint64_t* out_d, uint64_t* ws_d,
+                         void* stream) {
+    return guard([&] {
+        Hks& h = *hks->h;
+        use(h.ring);
+        OFHE_REQUIRE(k_in_h && k_out_h && evk_in_h && evk_out_h && A_d && ct_d && out_d && ws_d, "null argument");
+        OFHE_REQUIRE(g >= 1 && g <= 64 && b >= 1 && b <= 64, "bsgs: step counts out of range");
+        std::vector<const EvalKey*> ki(g, nullptr), ko(b, nullptr);
+        for (uint32_t j = 0; j < g; ++j) {
+            OFHE_REQUIRE(k_in_h[j] == 0 || ((k_in_h[j] & 1) && k_in_h[j] < 2 * h.ring->N && evk_in_h[j]),
+                         "bsgs: baby-step automorphism index must be 0 or odd and below 2N, with a key");
+            ki[j] = k_in_h[j] ? evk_in_h[j]->k : nullptr;
+        }
+        for (uint32_t i = 0; i < b; ++i) {
+            OFHE_REQUIRE(k_out_h[i] == 0 || ((k_out_h[i] & 1) && k_out_h[i] < 2 * h.ring->N && evk_out_h[i]),
+                         "bsgs: giant-step automorphism index must be 0 or odd and below 2N, with a key");
+            ko[i] = k_out_h[i] ? evk_out_h[i]->k : nullptr;
+        }
+        h.bsgs_level(sizeQl, g, b, k_in_h, k_out_h, ki.data(), ko.data(), A_d, skip, ct_d, out_d, ws_d, S(stream));
+    });
+}
 uint32_t ofhe_find_automorphism_index(int32_t index, uint32_t m) {
     // FindAutomorphismIndex2nComplex (core/lib/math/nbtheory2.cpp:243-262): 5^index mod m (5^-1 for negative index)
     if (index == 0)

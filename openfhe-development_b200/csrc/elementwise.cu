@@ -162,16 +162,20 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(RingDev r, uint32_t nd, c
                                                         size_t dstride, const uint64_t* __restrict__ ea,
                                                         const uint64_t* __restrict__ eb, size_t estride,
                                                         uint32_t sizeQl, uint32_t delta, uint64_t* __restrict__ e0,
-                                                        uint64_t* __restrict__ e1, LimbMap lm) {
+                                                        uint64_t* __restrict__ e1, LimbMap lm,
+                                                        const uint64_t* __restrict__ c_own, uint32_t alpha) {
     const uint32_t limb = blockIdx.y;
     const ModConst mc   = r.mc[lm.idx[limb]];
     const uint32_t kidx = limb >= sizeQl ? limb + delta : limb;
     const size_t half   = r.N >> 1;
     const size_t doff = (size_t)limb * half, eoff = (size_t)kidx * half;
+    // c_own: digit j's OWN rows (limbs [j alpha, (j+1) alpha) of Ql) are the original limbs of the switched polynomial
+    // (keyswitch-hybrid.cpp:372-373); read them from there instead of from copies inside the digit slabs
+    const uint32_t own = (c_own && limb < sizeQl) ? limb / alpha : 0xffffffffu;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
         unsigned __int128 s0x = 0, s0y = 0, s1x = 0, s1y = 0;
         for (uint32_t j = 0; j < nd; ++j) {
-            v2 d = ldv(digits + j * dstride, doff + i);
+            v2 d = ldv(j == own ? c_own : digits + j * dstride, doff + i);
             v2 b = ldv(eb + j * estride, eoff + i);
             v2 a = ldv(ea + j * estride, eoff + i);
             s0x += (unsigned __int128)d.x * b.x;
@@ -295,11 +299,12 @@ void launch_automorphism_coeff(const Ring& r, uint64_t* dst, const uint64_t* src
 }
 void launch_ks_inner_product(const Ring& r, uint32_t nd, const uint64_t* digits, size_t dstride,
                              const uint64_t* evk_a, const uint64_t* evk_b, size_t estride, uint32_t sizeQl,
-                             uint32_t delta, uint64_t* e0, uint64_t* e1, const LimbMap& lm, cudaStream_t st) {
+                             uint32_t delta, uint64_t* e0, uint64_t* e1, const LimbMap& lm, cudaStream_t st,
+                             const uint64_t* c_own, uint32_t alpha) {
     if (lm.n == 0)
         return;
     ks_inner_kernel<<<ew_grid(r, lm.n, r.N / 2), 256, 0, st>>>(r.dev(), nd, digits, dstride, evk_a, evk_b, estride,
-                                                               sizeQl, delta, e0, e1, lm);
+                                                               sizeQl, delta, e0, e1, lm, c_own, alpha ? alpha : 1);
     OFHE_CUDA(cudaGetLastError());
 }
 void launch_tensor(const Ring& r, const uint64_t* a0, const uint64_t* a1, const uint64_t* b0, const uint64_t* b1,

@@ -225,7 +225,8 @@ size_t Hks::max_workspace_words(uint32_t sizeQl) const {
     return std::max(workspace_words(sizeQl) + 2 * P, 2 * E + 2 * sizeP * N + 4 * P);
 }
 
-void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st) {
+void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st,
+                bool own_rows) {
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, sizeQlP = sizeQl + sizeP;
@@ -236,23 +237,25 @@ void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* 
         const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
         // 2. fast base conversion straight into the complementary rows of D_j           (:360-365)
         launch_bconv(r, *lv.modup[j], coeff_tmp, D, 1, 0, 0, /*premultiplied=*/true, st);
-        // 3. the digit's own rows keep the ORIGINAL evaluation-format limbs of c          (:372-373)
-        OFHE_CUDA(cudaMemcpyAsync(D + (size_t)s * N, c + (size_t)s * N, sizeof(uint64_t) * ds * N,
-                                  cudaMemcpyDeviceToDevice, st));
+        // 3. the digit's own rows keep the ORIGINAL evaluation-format limbs of c          (:372-373); inside the fused
+        //    key switch the inner product reads them from c directly and the copies are skipped
+        if (own_rows)
+            OFHE_CUDA(cudaMemcpyAsync(D + (size_t)s * N, c + (size_t)s * N, sizeof(uint64_t) * ds * N,
+                                      cudaMemcpyDeviceToDevice, st));
     }
     // 4. one launch transforms every converted row of every digit back to EVALUATION      (:366)
     launch_ntt_fwd(r, digits, digits, lv.map_modup_ntt, st);
 }
 
 void Hks::inner_product(uint32_t sizeQl, uint32_t n_digits, const uint64_t* digits, const EvalKey& evk, uint64_t* e01,
-                        cudaStream_t st) {
+                        cudaStream_t st, const uint64_t* c_own) {
     Level& lv      = level(sizeQl);
     const Ring& r  = *ring;
     const size_t N = r.N, sizeQlP = sizeQl + sizeP, sizeQP = sizeQ + sizeP;
     OFHE_REQUIRE(evk.hks == this, "evaluation key belongs to a different key-switch context");
     OFHE_REQUIRE(n_digits <= evk.dnum, "more digits than the evaluation key holds");
     launch_ks_inner_product(r, n_digits, digits, sizeQlP * N, evk.a_d, evk.b_d, sizeQP * N, sizeQl, sizeQ - sizeQl, e01,
-                            e01 + sizeQlP * N, lv.map_QlP, st);
+                            e01 + sizeQlP * N, lv.map_QlP, st, c_own, alpha);
 }
 
 void Hks::mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const uint64_t* addend01, uint64_t* p_tmp,
@@ -289,8 +292,8 @@ void Hks::keyswitch_core(uint32_t sizeQl, const uint64_t* c, const EvalKey& evk,
     uint64_t* e01    = digits + (size_t)dnum * sizeQlP * N;
     uint64_t* p_tmp  = e01 + 2 * sizeQlP * N;
     uint64_t* conv   = p_tmp + 2 * (size_t)sizeP * N;
-    modup(sizeQl, c, digits, coeff, st);
-    inner_product(sizeQl, lv.n_digits, digits, evk, e01, st);
+    modup(sizeQl, c, digits, coeff, st, /*own_rows=*/false);
+    inner_product(sizeQl, lv.n_digits, digits, evk, e01, st, /*c_own=*/c);
     mod_down2(sizeQl, e01, out01, addend01, p_tmp, conv, st);
 }
 
@@ -388,6 +391,88 @@ void Hks::keyswitch_ext(uint32_t sizeQl, bool add_first, const uint64_t* ct, uin
     OFHE_CUDA(cudaMemsetAsync(out_ext, 0, sizeof(uint64_t) * 2 * E, st));
     for (uint32_t b = add_first ? 0 : 1; b < 2; ++b)
         launch_mul_scalars(r, out_ext + b * E, ct + b * P, pmodq_sv, lv.map_Ql, st);
+}
+
+// ---- double-hoisted BSGS linear transform, one level ------------------------------------------------------------
+// Reference: the body of the `for s` loops of FHECKKSRNS::EvalCoeffsToSlots (ckksrns-fhe.cpp:1934-1987) and
+// EvalSlotsToCoeffs (:2094-2139); EvalLinearTransform (:1834-1882) is the same scheme with single hoisting.
+//   digits      = EvalFastRotationPrecompute(ct)                                              (:1941)
+//   fr[j]       = k_in[j] != 0 ? EvalFastRotationExt(ct, k_in[j], digits, addFirst = true)
+//                              : KeySwitchExt(ct, addFirst = true)                            (:1943-1946)  [2][QlP][N]
+//   for i < b:  inner = sum_j fr[j] (.) A[g i + j]   (EvalMultExt / EvalAddExtInPlace, j with g i + j == skip left out)
+//               i == 0        : first = KeySwitchDownFirstElement(inner); outer = inner with element 0 zeroed
+//               k_out[i] != 0 : inner' = KeySwitchDown(inner); first += auto_k(inner'_0);
+//                               outer += EvalFastRotationExt(inner', k_out[i], Precompute(inner'), addFirst = false)
+//               k_out[i] == 0 : first += KeySwitchDownFirstElement(inner); outer += inner with element 0 zeroed
+//   out = KeySwitchDown(outer); out_0 += first                                               (:1984-1985)
+// k_in / k_out are AUTOMORPHISM indices (FindAutomorphismIndex2nComplex of the rotation; 0 = no rotation); A holds the
+// b*g pre-encoded diagonals in the extended basis, [b*g][sizeQl+sizeP][N] EVALUATION, device resident.
+// Nothing leaves the device and nothing is allocated: `ws` is the caller's, bsgs_workspace_words() words.
+size_t Hks::bsgs_workspace_words(uint32_t sizeQl, uint32_t g) const {
+    const size_t N = ring->N, Ql = sizeQl, QlP = sizeQl + sizeP;
+    //  digits, inner digits | coeff tmp, first, auto tmp, inner' (2) | fr (2g), inner, outer, rotated (2 each) | P rows (2), conv (2)
+    return N * (2 * (size_t)dnum * QlP + 5 * Ql + (2 * (size_t)g + 6) * QlP + 2 * sizeP + 2 * Ql);
+}
+
+void Hks::bsgs_level(uint32_t sizeQl, uint32_t g, uint32_t b, const uint32_t* k_in, const uint32_t* k_out,
+                     const EvalKey* const* evk_in, const EvalKey* const* evk_out, const uint64_t* A, uint32_t skip,
+                     const uint64_t* ct, uint64_t* out, uint64_t* ws, cudaStream_t st) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, P = (size_t)sizeQl * N, E = (size_t)(sizeQl + sizeP) * N;
+    OFHE_REQUIRE(g >= 1 && b >= 1, "bsgs: empty step counts");
+    uint64_t* digits = ws;
+    uint64_t* idig   = digits + (size_t)dnum * E;
+    uint64_t* coeff  = idig + (size_t)dnum * E;
+    uint64_t* first  = coeff + P;
+    uint64_t* atmp   = first + P;
+    uint64_t* innerD = atmp + P;           // [2][sizeQl][N]
+    uint64_t* fr     = innerD + 2 * P;     // [g][2][QlP][N]
+    uint64_t* inner  = fr + 2 * (size_t)g * E;
+    uint64_t* outer  = inner + 2 * E;
+    uint64_t* rot    = outer + 2 * E;
+    uint64_t* p_tmp  = rot + 2 * E;
+    uint64_t* conv   = p_tmp + 2 * (size_t)sizeP * N;
+    // hoisting: one ModUp of c1 for all g baby-step rotations
+    modup(sizeQl, ct + P, digits, coeff, st);
+    for (uint32_t j = 0; j < g; ++j) {
+        if (k_in[j] != 0)
+            fast_rotation_ext(sizeQl, k_in[j], true, ct, digits, *evk_in[j], fr + 2 * (size_t)j * E, st);
+        else
+            keyswitch_ext(sizeQl, true, ct, fr + 2 * (size_t)j * E, st);
+    }
+    for (uint32_t i = 0; i < b; ++i) {
+        const uint32_t G = g * i;
+        for (uint32_t j = 0; j < g; ++j) {
+            if (j != 0 && G + j == skip)
+                continue;
+            const uint64_t* a = A + (size_t)(G + j) * E;
+            for (uint32_t e = 0; e < 2; ++e)   // EvalMultExt: both elements times the same plaintext (:2267-2276)
+                launch_ew(r, j == 0 ? EW_MUL : EW_MAC, inner + e * E, fr + (2 * (size_t)j + e) * E, a, lv.map_QlP, st);
+        }
+        if (i == 0) {
+            mod_down2(sizeQl, inner, innerD, nullptr, p_tmp, conv, st);  // only element 0 is kept here
+            OFHE_CUDA(cudaMemcpyAsync(first, innerD, sizeof(uint64_t) * P, cudaMemcpyDeviceToDevice, st));
+            OFHE_CUDA(cudaMemsetAsync(outer, 0, sizeof(uint64_t) * E, st));
+            OFHE_CUDA(cudaMemcpyAsync(outer + E, inner + E, sizeof(uint64_t) * E, cudaMemcpyDeviceToDevice, st));
+        }
+        else if (k_out[i] != 0) {
+            mod_down2(sizeQl, inner, innerD, nullptr, p_tmp, conv, st);                       // KeySwitchDown
+            launch_automorphism(r, atmp, innerD, ring_automap(ring, k_out[i], st), sizeQl, st);
+            launch_ew(r, EW_ADD, first, first, atmp, lv.map_Ql, st);
+            modup(sizeQl, innerD + P, idig, coeff, st);                                        // second hoisting
+            fast_rotation_ext(sizeQl, k_out[i], false, innerD, idig, *evk_out[i], rot, st);
+            for (uint32_t e = 0; e < 2; ++e)
+                launch_ew(r, EW_ADD, outer + e * E, outer + e * E, rot + e * E, lv.map_QlP, st);
+        }
+        else {
+            mod_down2(sizeQl, inner, innerD, nullptr, p_tmp, conv, st);
+            launch_ew(r, EW_ADD, first, first, innerD, lv.map_Ql, st);
+            launch_ew(r, EW_ADD, outer + E, outer + E, inner + E, lv.map_QlP, st);           // element 0 contributes zero
+        }
+    }
+    mod_down2(sizeQl, outer, out, nullptr, p_tmp, conv, st);
+    launch_ew(r, EW_ADD, out, out, first, lv.map_Ql, st);
 }
 
 EvalKey::~EvalKey() {

@@ -50,10 +50,13 @@ struct Hks {
     size_t max_workspace_words(uint32_t sizeQl) const;  // the largest arena any entry point asks for at this level
 
     // c [sizeQl][N] EVALUATION -> digits [n_digits][sizeQl+sizeP][N] EVALUATION; coeff_tmp [sizeQl][N] scratch
-    void modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st);
+    // own_rows = false: the digit slabs do NOT receive the digit's own (original) rows -- only for a caller that hands
+    // the switched polynomial to inner_product() as c_own
+    void modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* coeff_tmp, cudaStream_t st,
+               bool own_rows = true);
     // e01 [2][sizeQl+sizeP][N]
     void inner_product(uint32_t sizeQl, uint32_t n_digits, const uint64_t* digits, const EvalKey& evk, uint64_t* e01,
-                       cudaStream_t st);
+                       cudaStream_t st, const uint64_t* c_own = nullptr);
     // e01 [2][sizeQl+sizeP][N] -> out01 [2][sizeQl][N] (+ addend01 if given; may alias out01)
     void mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const uint64_t* addend01, uint64_t* p_tmp,
                    uint64_t* conv_tmp, cudaStream_t st);
@@ -70,6 +73,13 @@ struct Hks {
     void fast_rotation_ext(uint32_t sizeQl, uint32_t k, bool add_first, const uint64_t* ct, const uint64_t* digits,
                            const EvalKey& evk, uint64_t* out_ext, cudaStream_t st);
     void keyswitch_ext(uint32_t sizeQl, bool add_first, const uint64_t* ct, uint64_t* out_ext, cudaStream_t st);
+    // One level of the double-hoisted baby-step / giant-step linear transform: the loop body of
+    // FHECKKSRNS::EvalCoeffsToSlots / EvalSlotsToCoeffs (pke/lib/scheme/ckksrns/ckksrns-fhe.cpp:1934-1987, 2094-2139)
+    // with every intermediate device resident.  See hks.cu.
+    size_t bsgs_workspace_words(uint32_t sizeQl, uint32_t g) const;
+    void bsgs_level(uint32_t sizeQl, uint32_t g, uint32_t b, const uint32_t* k_in, const uint32_t* k_out,
+                    const EvalKey* const* evk_in, const EvalKey* const* evk_out, const uint64_t* A, uint32_t skip,
+                    const uint64_t* ct, uint64_t* out, uint64_t* ws, cudaStream_t st);
     ScalarVec pmodq_sv;  // P mod q_i with Shoup constants (GetPModq, rns-cryptoparameters.h)
 };
 

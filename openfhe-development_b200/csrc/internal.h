@@ -186,7 +186,10 @@ void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* o
 // hybrid key-switch inner product (a17)
 void launch_ks_inner_product(const Ring& r, uint32_t n_digits, const uint64_t* digits, size_t digit_stride,
                              const uint64_t* evk_a, const uint64_t* evk_b, size_t evk_stride, uint32_t sizeQl,
-                             uint32_t delta, uint64_t* e0, uint64_t* e1, const LimbMap& lm, cudaStream_t st);
+                             uint32_t delta, uint64_t* e0, uint64_t* e1, const LimbMap& lm, cudaStream_t st,
+                             const uint64_t* c_own = nullptr, uint32_t alpha = 0);
+// c_own != nullptr: digit j's own rows [j alpha, (j+1) alpha) are read from the switched polynomial c_own [sizeQl][N]
+// instead of from the digit slabs (which then need not hold them)
 // EvalMultCore tensor (a19): c0=a0*b0, c1=a0*b1+a1*b0, c2=a1*b1
 void launch_tensor(const Ring& r, const uint64_t* a0, const uint64_t* a1, const uint64_t* b0, const uint64_t* b1,
                    uint64_t* c0, uint64_t* c1, uint64_t* c2, const LimbMap& lm, cudaStream_t st);

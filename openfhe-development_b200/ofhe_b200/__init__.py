@@ -71,6 +71,9 @@ SIGNATURES = {
     "ofhe_ckks_rotate": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_ckks_fast_rotation": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_ckks_fast_rotation_ext": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_ckks_bsgs_workspace_words": (C.c_size_t, [_vp, C.c_uint32, C.c_uint32]),
+    "ofhe_ckks_bsgs_level": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp,
+                                       _vp, _vp, _vp]),
     "ofhe_hks_keyswitch_ext": (C.c_int, [_vp, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "ofhe_find_automorphism_index": (C.c_uint32, [C.c_int32, C.c_uint32]),
     "ofhe_ckks_paramgen": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp,
@@ -561,6 +564,21 @@ class Hks:
     def fast_rotation_ext(self, sizeQl, k, add_first, ct, digits, evk, out_ext):
         _ck(lib().ofhe_ckks_fast_rotation_ext(self.h, sizeQl, k, int(add_first), _ptr(ct), _ptr(digits), evk.h,
                                               _ptr(out_ext), _stream()))
+
+    def bsgs_workspace(self, sizeQl, g):
+        """device workspace for bsgs_level (caller-owned, reusable)"""
+        words = lib().ofhe_ckks_bsgs_workspace_words(self.h, sizeQl, g)
+        return self.ring.ctx.zeros(words)
+
+    def bsgs_level(self, sizeQl, k_in, k_out, evk_in, evk_out, A, skip, ct, out, ws):
+        """One level of the double-hoisted BSGS linear transform (ckksrns-fhe.cpp:1934-1987), device resident.
+        k_*: automorphism indices (0 = no rotation); evk_*: EvalKey or None per step; A [b*g][sizeQl+sizeP][N]."""
+        g, b = len(k_in), len(k_out)
+        ki, ko = _idx(k_in), _idx(k_out)
+        pin = (_vp * g)(*[(e.h if e is not None else None) for e in evk_in])
+        pout = (_vp * b)(*[(e.h if e is not None else None) for e in evk_out])
+        _ck(lib().ofhe_ckks_bsgs_level(self.h, sizeQl, g, b, ki.ctypes.data, ko.ctypes.data, pin, pout, _ptr(A), skip,
+                                       _ptr(ct), _ptr(out), _ptr(ws), _stream()))
 
     def keyswitch_ext(self, sizeQl, add_first, ct, out_ext):
         _ck(lib().ofhe_hks_keyswitch_ext(self.h, sizeQl, int(add_first), _ptr(ct), _ptr(out_ext), _stream()))

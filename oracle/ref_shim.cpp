@@ -664,6 +664,72 @@ int ref_ckks_keyswitch_down(void* hv, uint32_t sizeQl, const uint64_t* ct_ext, u
         dump_poly(c->GetElements()[1], out + (size_t)sizeQl * h->N);
     });
 }
+// One level of the double-hoisted BSGS linear transform, run with the reference's OWN primitives in the order of
+// FHECKKSRNS::EvalCoeffsToSlots' loop body (ckksrns-fhe.cpp:1934-1987): cc->EvalFastRotationPrecompute,
+// cc->EvalFastRotationExt, cc->KeySwitchExt, cc->KeySwitchDown, cc->KeySwitchDownFirstElement; EvalMultExt /
+// EvalAddExtInPlace (protected members of FHECKKSRNS, :2267-2290) are the element-wise products / sums they consist of.
+// rot_in[g] / rot_out[b]: ROTATION indices (0 = none; keys must exist: ref_ckks_rotate_key); A: [b*g][sizeQl+sizeP][N]
+// diagonals in the extended basis (EVALUATION); ct [2][sizeQl][N] -> out [2][sizeQl][N].
+int ref_ckks_bsgs_level(void* hv, uint32_t sizeQl, uint32_t g, uint32_t b, const int32_t* rot_in, const int32_t* rot_out,
+                        const uint64_t* A, uint32_t skip, const uint64_t* ct, uint64_t* out) {
+    auto* h = static_cast<CkksCtx*>(hv);
+    return guarded([&] {
+        auto cc       = h->cc;
+        const size_t E = (size_t)(sizeQl + h->sizeP) * h->N;
+        auto result   = make_ct(h, sizeQl, ct, 2);
+        auto digits   = cc->EvalFastRotationPrecompute(result);
+        std::vector<Ciphertext<DCRTPoly>> fr(g);
+        for (uint32_t j = 0; j < g; ++j)
+            fr[j] = (rot_in[j] != 0) ? cc->EvalFastRotationExt(result, rot_in[j], digits, true) : cc->KeySwitchExt(result, true);
+        const auto paramsQlP = fr[0]->GetElements()[0].GetParams();
+        auto multExt = [&](ConstCiphertext<DCRTPoly> c, uint32_t idx) {
+            auto r = c->Clone();
+            DCRTPoly pt = make_poly(paramsQlP, Format::EVALUATION, A + (size_t)idx * E);
+            for (auto& e : r->GetElements())
+                e *= pt;
+            return r;
+        };
+        auto addExt = [&](Ciphertext<DCRTPoly>& a, ConstCiphertext<DCRTPoly> c) {
+            auto& av = a->GetElements();
+            const auto& cv = c->GetElements();
+            for (size_t i = 0; i < av.size(); ++i)
+                av[i] += cv[i];
+        };
+        const uint32_t N = h->N;
+        std::vector<uint32_t> map(N);
+        Ciphertext<DCRTPoly> outer;
+        DCRTPoly first;
+        for (uint32_t i = 0; i < b; ++i) {
+            const uint32_t G = g * i;
+            auto inner = multExt(fr[0], G);
+            for (uint32_t j = 1; j < g; ++j)
+                if (G + j != skip)
+                    addExt(inner, multExt(fr[j], G + j));
+            if (i == 0) {
+                first = cc->KeySwitchDownFirstElement(inner);
+                outer = std::move(inner);
+                outer->GetElements()[0].SetValuesToZero();
+            }
+            else if (rot_out[i] != 0) {
+                inner = cc->KeySwitchDown(inner);
+                uint32_t autoIndex = FindAutomorphismIndex2nComplex(rot_out[i], cc->GetCyclotomicOrder());
+                PrecomputeAutoMap(N, autoIndex, &map);
+                first += inner->GetElements()[0].AutomorphismTransform(autoIndex, map);
+                auto innerDigits = cc->EvalFastRotationPrecompute(inner);
+                addExt(outer, cc->EvalFastRotationExt(inner, rot_out[i], innerDigits, false));
+            }
+            else {
+                first += cc->KeySwitchDownFirstElement(inner);
+                inner->GetElements()[0].SetValuesToZero();
+                addExt(outer, inner);
+            }
+        }
+        result = cc->KeySwitchDown(outer);
+        result->GetElements()[0] += first;
+        dump_poly(result->GetElements()[0], out);
+        dump_poly(result->GetElements()[1], out + (size_t)sizeQl * h->N);
+    });
+}
 // honest end-to-end check material: encrypt a real vector, return its towers; decrypt towers back.
 int ref_ckks_encrypt(void* hv, const double* vals, uint32_t n, uint64_t* out) {
     auto* h = static_cast<CkksCtx*>(hv);

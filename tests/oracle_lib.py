@@ -353,6 +353,41 @@ class OracleCkks(_CkksCommon):
         self.L.orc_ckks_keyswitch_down(self.h, sizeQl, np.ascontiguousarray(ct_ext), out)
         return out
 
+    def bsgs_level(self, sizeQl, k_in, k_out, keys_in, keys_out, A, skip, ct, binop):
+        """One level of the double-hoisted BSGS linear transform, composed from the oracle's primitives in the order
+        of FHECKKSRNS::EvalCoeffsToSlots' loop body (ckksrns-fhe.cpp:1934-1987).  k_*: automorphism indices (0 = no
+        rotation), keys_*: (evk_a, evk_b) per step, A: [b*g][sizeQl+sizeP][N], binop(q, op, a, b): limb-wise op."""
+        g, b = len(k_in), len(k_out)
+        qlp = np.concatenate([self.moduli[:sizeQl], self.moduli[self.sizeQ:]])
+        ql = self.moduli[:sizeQl]
+        digits = self.modup(sizeQl, ct[1])
+        fr = [self.fast_rotation_ext(sizeQl, k_in[j], True, ct, digits, *keys_in[j]) if k_in[j] else
+              self.keyswitch_ext(sizeQl, True, ct) for j in range(g)]
+        first = outer = None
+        for i in range(b):
+            G = g * i
+            inner = np.stack([binop(qlp, 2, fr[0][e], A[G]) for e in range(2)])
+            for j in range(1, g):
+                if G + j != skip:
+                    inner = np.stack([binop(qlp, 0, inner[e], binop(qlp, 2, fr[j][e], A[G + j])) for e in range(2)])
+            if i == 0:
+                first = self.keyswitch_down(sizeQl, inner)[0]
+                outer = inner.copy()
+                outer[0] = 0
+            elif k_out[i]:
+                d = self.keyswitch_down(sizeQl, inner)
+                m = np.empty(self.N, dtype=np.uint32)
+                self.L.orc_automorphism_map(self.N, k_out[i], m)
+                first = binop(ql, 0, first, np.ascontiguousarray(d[0][:, m]))
+                rot = self.fast_rotation_ext(sizeQl, k_out[i], False, d, self.modup(sizeQl, d[1]), *keys_out[i])
+                outer = np.stack([binop(qlp, 0, outer[e], rot[e]) for e in range(2)])
+            else:
+                first = binop(ql, 0, first, self.keyswitch_down(sizeQl, inner)[0])
+                outer[1] = binop(qlp, 0, outer[1], inner[1])
+        res = self.keyswitch_down(sizeQl, outer)
+        res[0] = binop(ql, 0, res[0], first)
+        return res
+
 
 class Reference:
     """The unmodified reference behind oracle/ref_shim.cpp."""
@@ -383,6 +418,9 @@ class Reference:
         _sig(L, "ref_dcrt_serialize", C.c_size_t, C.c_uint32, C.c_uint32, u64p, u64p, C.c_int, u64p, C.c_int,
              C.c_void_p, C.c_size_t)
         _sig(L, "ref_dcrt_automorphism", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p)
+        _sig(L, "ref_ckks_bsgs_level", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+             np.ctypeslib.ndpointer(np.int32, flags="C"), np.ctypeslib.ndpointer(np.int32, flags="C"), u64p, C.c_uint32,
+             u64p, u64p)
         _sig(L, "ref_dcrt_automorphism_coeff", C.c_int, C.c_uint32, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p)
         _sig(L, "ref_automorphism_map", C.c_int, C.c_uint32, C.c_uint32, u32p)
         _sig(L, "ref_switch_modulus", C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, u64p)
@@ -648,6 +686,15 @@ class ReferenceCkks(_CkksCommon):
     def keyswitch_down(self, sizeQl, ct_ext):
         out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
         self.r._ok(self.L.ref_ckks_keyswitch_down(self.h, sizeQl, np.ascontiguousarray(ct_ext), out))
+        return out
+
+    def bsgs_level(self, sizeQl, rot_in, rot_out, A, skip, ct):
+        """rot_*: ROTATION indices (keys generated beforehand with rotate_key)."""
+        out = np.empty((2, sizeQl, self.N), dtype=np.uint64)
+        self.r._ok(self.L.ref_ckks_bsgs_level(self.h, sizeQl, len(rot_in), len(rot_out),
+                                              np.ascontiguousarray(rot_in, dtype=np.int32),
+                                              np.ascontiguousarray(rot_out, dtype=np.int32), np.ascontiguousarray(A),
+                                              skip, np.ascontiguousarray(ct), out))
         return out
 
     def encrypt(self, vals):

@@ -558,3 +558,45 @@ def test_upload_cereal_archive(gpu):
         ring.upload_cereal(m.cereal_write_dcrtpoly(q, roots, 0, bad))
     slab3, _ = ring.upload_cereal(m.cereal_write_dcrtpoly(q, roots, 0, bad), check_residues=False)
     assert (ctx.download(slab3) == bad).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,lvl_drop", [((1 << 10, 5, 45, 55, 3, 1), 0), ((1 << 12, 4, 50, 60, 2, 0), 1)])
+def test_bsgs_linear_transform_level(gpu, oracle, args, lvl_drop):
+    """ofhe_ckks_bsgs_level (double-hoisted baby-step / giant-step level, ckksrns-fhe.cpp:1934-1987) with
+    every intermediate on the device, bit-exact against the oracle's composition (itself pinned to the reference's own
+    primitives run in that order, tests/test_oracle_vs_reference.py::test_bsgs_linear_transform_level)."""
+    ctx, m = gpu
+    N = args[0]
+    c = oracle.ckks(*args)
+    try:
+        p = m.ckks_paramgen(*args)
+        ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+        hks = m.Hks(ring, p["sizeQ"], p["sizeP"], p["dnum"])
+        sizeQl = c.sizeQ - lvl_drop
+        rot_in, rot_out = [-1, 0, 1, 2], [0, 4, 0, 8]
+        g, b = len(rot_in), len(rot_out)
+        keymod = np.tile(c.moduli, c.dnum)
+        host_keys, dev_keys = {}, {}
+        for n, idx in enumerate(sorted(set(rot_in + rot_out) - {0})):
+            ka = seeded_residues(200 + 2 * n, keymod, N).reshape(c.dnum, c.sizeQP, N)
+            kb = seeded_residues(201 + 2 * n, keymod, N).reshape(c.dnum, c.sizeQP, N)
+            host_keys[idx] = (ka, kb)
+            dev_keys[idx] = m.EvalKey(hks, ka, kb)
+        k_of = lambda i: m.find_automorphism_index(i, 2 * N) if i else 0  # noqa: E731
+        k_in, k_out = [k_of(i) for i in rot_in], [k_of(i) for i in rot_out]
+        qlp = c.moduli_QlP(sizeQl)
+        A = np.stack([seeded_residues(100 + d, qlp, N) for d in range(b * g)])
+        ct = np.stack([seeded_residues(31, c.moduli[:sizeQl], N), seeded_residues(32, c.moduli[:sizeQl], N)])
+        skip = b * g - 2
+        want = c.bsgs_level(sizeQl, k_in, k_out, [host_keys.get(i) for i in rot_in], [host_keys.get(i) for i in rot_out],
+                            A, skip, ct, oracle.dcrt_binop)
+        out = ctx.zeros(2, sizeQl, N)
+        ws = hks.bsgs_workspace(sizeQl, g)
+        hks.bsgs_level(sizeQl, k_in, k_out, [dev_keys.get(i) for i in rot_in], [dev_keys.get(i) for i in rot_out],
+                       ctx.upload(A), skip, ctx.upload(ct), out, ws)
+        assert (ctx.download(out) == want).all()
+        for o in list(dev_keys.values()) + [hks, ring]:
+            o.close()
+    finally:
+        c.close()

@@ -133,6 +133,36 @@ def test_ckks_tables_and_keyswitch(oracle, reference, args):
         rc.close()
 
 
+@pytest.mark.parametrize("args,lvl_drop", [((1 << 9, 4, 50, 60, 2, 0), 0), ((1 << 10, 5, 45, 55, 3, 1), 1)])
+def test_bsgs_linear_transform_level(oracle, reference, args, lvl_drop):
+    """one level of the double-hoisted baby-step / giant-step linear transform (the loop body of
+    FHECKKSRNS::EvalCoeffsToSlots, ckksrns-fhe.cpp:1934-1987).  The reference side runs the reference's OWN primitives
+    in that order (oracle/ref_shim.cpp:ref_ckks_bsgs_level); the oracle side composes its restated primitives."""
+    N = args[0]
+    oc, rc = oracle.ckks(*args), reference.ckks(*args)
+    try:
+        sizeQl = oc.sizeQ - lvl_drop
+        rot_in, rot_out = [-1, 0, 1, 2], [0, 4, 0, 8]  # a zero baby step (KeySwitchExt) and a zero giant step
+        g, b = len(rot_in), len(rot_out)
+        keys = {}
+        for idx in set(rot_in + rot_out) - {0}:
+            keys[idx] = rc.rotate_key(idx)  # (k, a, b)
+        k_in = [keys[i][0] if i else 0 for i in rot_in]
+        k_out = [keys[i][0] if i else 0 for i in rot_out]
+        keys_in = [keys[i][1:] if i else None for i in rot_in]
+        keys_out = [keys[i][1:] if i else None for i in rot_out]
+        qlp = oc.moduli_QlP(sizeQl)
+        A = np.stack([seeded_residues(100 + d, qlp, N) for d in range(b * g)])
+        ct = np.stack([seeded_residues(31, oc.moduli[:sizeQl], N), seeded_residues(32, oc.moduli[:sizeQl], N)])
+        skip = b * g - 2  # a left-out diagonal (the reference's `G + j != numRotations`)
+        want = rc.bsgs_level(sizeQl, rot_in, rot_out, A, skip, ct)
+        got = oc.bsgs_level(sizeQl, k_in, k_out, keys_in, keys_out, A, skip, ct, oracle.dcrt_binop)
+        assert (got == want).all()
+    finally:
+        oc.close()
+        rc.close()
+
+
 @pytest.mark.parametrize("args", [(1 << 16, 44, 59, 60, 0, 0), (1 << 12, 3, 45, 55, 0, 1), (1 << 13, 11, 50, 60, 4, 2),
                                   (1 << 11, 1, 30, 40, 0, 0), (1 << 12, 24, 59, 60, 3, 1), (1 << 12, 5, 50, 60, 0, 3),
                                   (1 << 16, 44, 59, 60, 0, 3), (1 << 11, 2, 40, 50, 2, 3)])

@@ -203,7 +203,22 @@ def config2_resident(m, torch, ctx):
     us = _timeit(torch, hoisted, 5)
     out["hoisted_8_rotations_us"] = us
     out["hoisted_rotations_per_s"] = R * 1e6 / us
-    for o in (evk, rk, hks, ring):
+    # one level of the double-hoisted BSGS linear transform (ofhe_ckks_bsgs_level, ckksrns-fhe.cpp:1934-1987):
+    # g = b = 8 (64 diagonals in QlP, 8 baby-step + 7 giant-step hoisted rotations, 9 ModDowns), synthetic keys
+    g = b = 8
+    Ls = L - 1
+    keys_in = [None] + [m.EvalKey(hks, seed=30 + j) for j in range(1, g)]
+    keys_out = [None] + [m.EvalKey(hks, seed=50 + i) for i in range(1, b)]
+    k_in = [0] + [m.find_automorphism_index(j, 2 * N) for j in range(1, g)]
+    k_out = [0] + [m.find_automorphism_index(g * i, 2 * N) for i in range(1, b)]
+    A = ctx.zeros(b * g, Ls + sizeP, N)
+    ring.fill_uniform(A.view(b * g * (Ls + sizeP), N), (list(range(Ls)) + list(range(L, L + sizeP))) * (b * g), 77)
+    ws = hks.bsgs_workspace(Ls, g)
+    res = ctx.zeros(2, Ls, N)
+    us = _timeit(torch, lambda: hks.bsgs_level(Ls, k_in, k_out, keys_in, keys_out, A, b * g, b_r, res, ws), 3, warm=1)
+    out["bsgs_level_g8_b8_us"] = us
+    out["bsgs_level_note"] = "64 plaintext diagonals, 15 hoisted rotations, device-resident accumulation in QlP (SURVEY 8 f2)"
+    for o in [k for k in keys_in + keys_out if k is not None] + [evk, rk, hks, ring]:
         o.close()
     return out
 
