@@ -556,6 +556,14 @@ def main():
             aux = aux_measurements(m, torch, ctx)
         except Exception as ex:  # side measurements never void the headline
             aux = {"error": repr(ex)}
+    if world > 1 and not a.no_aux:  # BASELINE config 5 at N GPUs (every rank takes part)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import aux_bench
+
+            aux = {"config5_ntt_sweep_limb_sharded": aux_bench.config5_sharded(m, torch, ctx, dist, rank, world)}
+        except Exception as ex:
+            aux = {"error": repr(ex)}
     if rank == 0:
         base = None
         if not a.no_cpu_baseline and world == 1:  # the CPU arm is timed at N=1 only (the ranks would fight for the cores)

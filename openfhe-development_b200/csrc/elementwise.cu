@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) ew_kernel(RingDev r, uint64_t* dst, const
     const ModConst mc   = r.mc[lm.idx[limb]];
     const uint64_t q    = mc.q;
     const size_t half   = r.N >> 1;
-    const size_t off    = (size_t)limb * half;
+    const size_t off    = (size_t)lm.pos[limb] * half;  // row of the slab (LimbMap: idx = modulus, pos = row)
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
         v2 x = ldv(a, off + i), o;
         if (OP == EW_NEG) {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) scal_kernel(RingDev r, uint64_t* dst, con
     const uint64_t q    = r.mc[lm.idx[limb]].q;
     const uint64_t s = sv.s[limb], ss = sv.ss[limb];
     const size_t half = r.N >> 1;
-    const size_t off  = (size_t)limb * half;
+    const size_t off  = (size_t)lm.pos[limb] * half;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
         v2 x = ldv(a, off + i), o;
         if (MODE == 0) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) switch_mod_kernel(RingDev r, uint64_t* __
             uint64_t bv = v > halfq ? diffr : 0;
             v           = av >= bv ? av - bv : av + qt - bv;
         }
-        dst[(size_t)limb * r.N + i] = shoup(v, s, ss, qt);
+        dst[(size_t)lm.pos[limb] * r.N + i] = shoup(v, s, ss, qt);
     }
 }
 
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) ks_inner_kernel(RingDev r, uint32_t nd, c
     const ModConst mc   = r.mc[lm.idx[limb]];
     const uint32_t kidx = limb >= sizeQl ? limb + delta : limb;
     const size_t half   = r.N >> 1;
-    const size_t doff = (size_t)limb * half, eoff = (size_t)kidx * half;
+    const size_t doff = (size_t)lm.pos[limb] * half, eoff = (size_t)kidx * half;
     // c_own: digit j's OWN rows (limbs [j alpha, (j+1) alpha) of Ql) are the original limbs of the switched polynomial
     // (keyswitch-hybrid.cpp:372-373); read them from there instead of from copies inside the digit slabs
     const uint32_t own = (c_own && limb < sizeQl) ? limb / alpha : 0xffffffffu;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) tensor_kernel(RingDev r, const uint64_t* 
     const uint32_t limb = blockIdx.y;
     const ModConst mc   = r.mc[lm.idx[limb]];
     const size_t half   = r.N >> 1;
-    const size_t off    = (size_t)limb * half;
+    const size_t off    = (size_t)lm.pos[limb] * half;  // row of the slab (LimbMap: idx = modulus, pos = row)
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
         v2 x0 = ldv(a0, off + i), x1 = ldv(a1, off + i), y0 = ldv(b0, off + i), y1 = ldv(b1, off + i);
         v2 o0, o1, o2;

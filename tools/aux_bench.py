@@ -212,7 +212,8 @@ def config2_resident(m, torch, ctx):
     k_in = [0] + [m.find_automorphism_index(j, 2 * N) for j in range(1, g)]
     k_out = [0] + [m.find_automorphism_index(g * i, 2 * N) for i in range(1, b)]
     A = ctx.zeros(b * g, Ls + sizeP, N)
-    ring.fill_uniform(A.view(b * g * (Ls + sizeP), N), (list(range(Ls)) + list(range(L, L + sizeP))) * (b * g), 77)
+    for d in range(b * g):  # one diagonal (Ls + sizeP limbs) per call: a launch addresses at most 256 limbs
+        ring.fill_uniform(A[d], list(range(Ls)) + list(range(L, L + sizeP)), 77 + d)
     ws = hks.bsgs_workspace(Ls, g)
     res = ctx.zeros(2, Ls, N)
     us = _timeit(torch, lambda: hks.bsgs_level(Ls, k_in, k_out, keys_in, keys_out, A, b * g, b_r, res, ws), 3, warm=1)
@@ -221,6 +222,38 @@ def config2_resident(m, torch, ctx):
     for o in [k for k in keys_in + keys_out if k is not None] + [evk, rk, hks, ring]:
         o.close()
     return out
+
+
+def config5_sharded(m, torch, ctx, dist, rank, world):
+    """BASELINE config 5 at N GPUs: the 256 limbs of every (N, L = 64, batch = 4) point are dealt round-robin to the
+    ranks (RNS limbs are independent: no exchange), every rank transforms its share, the time of a point is the MAX over
+    ranks (CUDA events, all_reduce), the throughput is the whole point's 16*N*256 bytes per direction over that time."""
+    peak = _peak()
+    rows = []
+    for logn in (12, 14, 16, 17):
+        N = 1 << logn
+        q, roots = m.dcrt_params(N, 64, 60)
+        ring = m.Ring(ctx, N, q, roots)
+        total = 256 if logn < 17 else 192
+        mine = [i % 64 for i in range(total) if i % world == rank]
+        idx = sorted(mine)
+        slab = ctx.zeros(len(idx), N)
+        ring.fill_uniform(slab, idx, 7)
+
+        def pair():
+            ring.ntt_fwd(slab, slab, idx)
+            ring.ntt_inv(slab, slab, idx)
+
+        dist.barrier()
+        us = torch.tensor([_timeit(torch, pair, 5, warm=2)], device=f"cuda:{ctx.device}", dtype=torch.float64)
+        dist.all_reduce(us, op=dist.ReduceOp.MAX)
+        gbs = 2 * 16.0 * N * total / float(us.item()) * 1e-3
+        rows.append({"logN": logn, "L": 64, "limbs_total": total, "limbs_per_rank": len(idx), "us_fwd_inv_pair_max_rank": float(us.item()),
+                     "gbs_all_ranks": round(gbs, 1), "frac_of_measured_hbm_x_ranks": round(gbs / (peak * world), 4)})
+        del slab
+        ring.close()
+    return {"workload": "batched DCRTPoly SwitchFormat (fwd + inv) with the limbs dealt to the ranks (no exchange), "
+                        "16*N*L algorithmic bytes per transform", "n_gpus": world, "peak_gbs_per_gpu": peak, "rows": rows}
 
 
 def run(m, torch, ctx):
