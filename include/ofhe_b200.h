@@ -43,6 +43,7 @@ int ofhe_free(ofhe_ctx* ctx, void* dptr);
 int ofhe_memcpy_h2d(ofhe_ctx* ctx, void* dst_d, const void* src_h, size_t bytes, void* stream);
 int ofhe_memcpy_d2h(ofhe_ctx* ctx, void* dst_h, const void* src_d, size_t bytes, void* stream);
 int ofhe_memcpy_d2d(ofhe_ctx* ctx, void* dst_d, const void* src_d, size_t bytes, void* stream);
+int ofhe_memset0(ofhe_ctx* ctx, void* dptr, size_t bytes, void* stream);
 int ofhe_stream_sync(ofhe_ctx* ctx, void* stream);
 /* One stream per calling thread: the reference's callers invoke DCRTPoly methods from inside their own
  * `omp parallel for` (pke/lib/keyswitch/keyswitch-hybrid.cpp:423, scheme/ckksrns/ckksrns-fhe.cpp:1943); every entry
@@ -77,6 +78,22 @@ int ofhe_ew_binop(ofhe_ring* ring, int op, uint64_t* dst_d, const uint64_t* a_d,
 /*          DCRTPolyImpl::Times(const std::vector<NativeInteger>&)          dcrtpoly-impl.h:553-567                */
 int ofhe_ew_mul_scalars(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* a_d, const uint64_t* scalars_h,
                         uint32_t n_limbs, const uint32_t* mod_idx_h, void* stream);
+/* ---- f4  BEHZ BFV: the per-coefficient corrections of DCRTPolyImpl::FastBaseConvqToBskMontgomery
+ *          (dcrtpoly-impl.h:1694-1777) and ::FastBaseConvSK (:1833-1921); their multiply-accumulate parts (and all of
+ *          ::FastRNSFloorq, :1780-1830) are table-driven base conversions: ofhe_bconv_create with the reference's tables.
+ *      mtilde    : r[k] = ((sum_i (x_i[k] * mtildeQHatInvModq_i mod q_i) * QHatModmtilde_i) mod 2^16) * negQInvModmtilde
+ *                  mod 2^16   -> r_out_d [N]                                                             (:1724-1738)
+ *      mtilde_fix: s_j[k] <- ((centre(r[k]) * QModbsk_j + s_j[k]) * mtildeInvModbsk_j) mod bsk_j, in place on
+ *                  s_d [n_bsk][N] (the converted residues)                                                (:1760-1767)
+ *      sk_fix    : q_j[k] <- q_j[k] - (lift(alpha[k]) * BModq_j) mod q_j, lift = the reference's ModSubFast(msk, q_j)
+ *                  for alpha > msk/2, in place on q_d [n_q][N]                                            (:1903-1907)  */
+int ofhe_behz_mtilde(ofhe_ring* ring, uint32_t n_q, const uint32_t* q_idx_h, const uint64_t* in_d,
+                     const uint64_t* mtildeQHatInvModq_h, const uint64_t* QHatModmtilde_h, uint64_t negQInvModmtilde,
+                     uint64_t* r_out_d, void* stream);
+int ofhe_behz_mtilde_fix(ofhe_ring* ring, uint32_t n_bsk, const uint32_t* bsk_idx_h, uint64_t* s_d, const uint64_t* r_d,
+                         const uint64_t* QModbsk_h, const uint64_t* mtildeInvModbsk_h, void* stream);
+int ofhe_behz_sk_fix(ofhe_ring* ring, uint32_t n_q, const uint32_t* q_idx_h, uint64_t* q_d, const uint64_t* alpha_d,
+                     uint64_t msk, const uint64_t* BModq_h, void* stream);
 /* ---- a4  NativeVectorT::SwitchModulus on one limb               math/hal/intnat/mubintvecnat.cpp:109-122        */
 int ofhe_switch_modulus(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t from_idx, uint32_t to_idx,
                         void* stream);

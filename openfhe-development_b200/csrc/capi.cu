@@ -133,6 +133,12 @@ int ofhe_memcpy_d2d(ofhe_ctx* ctx, void* d, const void* s, size_t bytes, void* s
         OFHE_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, S(stream)));
     });
 }
+int ofhe_memset0(ofhe_ctx* ctx, void* dptr, size_t bytes, void* stream) {
+    return guard([&] {
+        OFHE_CUDA(cudaSetDevice(ctx->c->device));
+        OFHE_CUDA(cudaMemsetAsync(dptr, 0, bytes, S(stream)));
+    });
+}
 int ofhe_stream_sync(ofhe_ctx* ctx, void* stream) {
     return guard([&] {
         OFHE_CUDA(cudaSetDevice(ctx->c->device));
@@ -239,6 +245,49 @@ int ofhe_ew_mul_scalars(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* a_d, c
             sv.ss[i]   = hm::shoup_const(sv.s[i], q);
         }
         launch_mul_scalars(*ring->r, dst_d, a_d, sv, lm, S(stream));
+    });
+}
+// ---- BEHZ correction steps (f4): see include/ofhe_b200.h
+static ScalarVec scalar_vec(const Ring* r, uint32_t n, const uint32_t* idx, const uint64_t* s_h) {
+    ScalarVec sv;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t q = r->moduli[idx[i]];
+        OFHE_REQUIRE(s_h[i] < q, "scalar is not reduced modulo its limb");
+        sv.s[i]  = s_h[i];
+        sv.ss[i] = hm::shoup_const(s_h[i], q);
+    }
+    return sv;
+}
+int ofhe_behz_mtilde(ofhe_ring* ring, uint32_t n_q, const uint32_t* q_idx_h, const uint64_t* in_d,
+                     const uint64_t* mtildeQHatInvModq_h, const uint64_t* QHatModmtilde_h, uint64_t negQInvModmtilde,
+                     uint64_t* r_out_d, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE(in_d && mtildeQHatInvModq_h && QHatModmtilde_h && r_out_d, "null argument");
+        LimbMap qm = checked_map(ring->r, n_q, q_idx_h);
+        ScalarVec hat = scalar_vec(ring->r, n_q, q_idx_h, mtildeQHatInvModq_h), qhm;
+        for (uint32_t i = 0; i < n_q; ++i)
+            qhm.s[i] = QHatModmtilde_h[i], qhm.ss[i] = 0;
+        launch_behz_mtilde(*ring->r, in_d, qm, hat, qhm, negQInvModmtilde, r_out_d, S(stream));
+    });
+}
+int ofhe_behz_mtilde_fix(ofhe_ring* ring, uint32_t n_bsk, const uint32_t* bsk_idx_h, uint64_t* s_d, const uint64_t* r_d,
+                         const uint64_t* QModbsk_h, const uint64_t* mtildeInvModbsk_h, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE(s_d && r_d && QModbsk_h && mtildeInvModbsk_h, "null argument");
+        LimbMap bm = checked_map(ring->r, n_bsk, bsk_idx_h);
+        launch_behz_mtilde_fix(*ring->r, s_d, bm, r_d, scalar_vec(ring->r, n_bsk, bsk_idx_h, QModbsk_h),
+                               scalar_vec(ring->r, n_bsk, bsk_idx_h, mtildeInvModbsk_h), S(stream));
+    });
+}
+int ofhe_behz_sk_fix(ofhe_ring* ring, uint32_t n_q, const uint32_t* q_idx_h, uint64_t* q_d, const uint64_t* alpha_d,
+                     uint64_t msk, const uint64_t* BModq_h, void* stream) {
+    return guard([&] {
+        use(ring->r);
+        OFHE_REQUIRE(q_d && alpha_d && BModq_h, "null argument");
+        LimbMap qm = checked_map(ring->r, n_q, q_idx_h);
+        launch_behz_sk_fix(*ring->r, q_d, qm, alpha_d, msk, scalar_vec(ring->r, n_q, q_idx_h, BModq_h), S(stream));
     });
 }
 int ofhe_switch_modulus(ofhe_ring* ring, uint64_t* dst_d, const uint64_t* src_d, uint32_t from_idx, uint32_t to_idx,

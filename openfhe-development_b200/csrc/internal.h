@@ -161,6 +161,14 @@ void launch_mul_scalars_add(const Ring& r, uint64_t* dst, const uint64_t* a, con
 void launch_sub_mul_scalars(const Ring& r, uint64_t* dst, const uint64_t* a, const uint64_t* b, const ScalarVec& sv,
                             const uint64_t* c, const LimbMap& lm, cudaStream_t st);
 
+// BEHZ correction steps (behz.cu): dcrtpoly-impl.h:1724-1738, 1760-1767, 1903-1907
+void launch_behz_mtilde(const Ring& r, const uint64_t* in, const LimbMap& qmap, const ScalarVec& hat, const ScalarVec& qhm,
+                        uint64_t neg_qinv, uint64_t* out, cudaStream_t st);
+void launch_behz_mtilde_fix(const Ring& r, uint64_t* s, const LimbMap& bmap, const uint64_t* rm, const ScalarVec& qmod,
+                            const ScalarVec& minv, cudaStream_t st);
+void launch_behz_sk_fix(const Ring& r, uint64_t* qc, const LimbMap& qmap, const uint64_t* alpha, uint64_t msk,
+                        const ScalarVec& bmod, cudaStream_t st);
+
 // fast base conversion tables (a10), device resident
 struct BConv {
     uint32_t sizeQ = 0, sizeP = 0;

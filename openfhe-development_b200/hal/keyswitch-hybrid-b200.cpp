@@ -11,11 +11,12 @@
 // in a COPY of its object file (objcopy --weaken-symbol) and links this translation unit next to it, so every caller
 // inside src/pke -- EvalMult's relinearisation, EvalRotate, EvalFastRotation, bootstrapping -- lands here.
 //
-// With the DCRTPoly backend alone each of these functions is a dozen separate DCRTPoly calls (every one an upload /
-// download through the host mirror) plus a tower-by-tower inner product on the host; here a key switch is ONE upload
-// of the polynomial, the fused device pipeline (ofhe_hks_*: INTT -> base conversion -> NTT -> inner product with the
-// DEVICE-RESIDENT evaluation key -> ModDown), and one download of the two result polynomials.  Evaluation keys are
-// uploaded once per EvalKey object and stay resident (a weak_ptr notices when the host object dies).
+// With the DCRTPoly backend alone each of these functions is a dozen separate DCRTPoly calls plus a tower-by-tower inner
+// product ON THE HOST (the reference multiplies NativePoly towers there); here a key switch is the fused device pipeline
+// (ofhe_hks_*: INTT -> base conversion -> NTT -> inner product with the DEVICE-RESIDENT evaluation key -> ModDown) from
+// the operand's device slab to device-resident results -- the digits of a hoisted rotation are views of one slab that
+// the next call consumes in place.  Evaluation keys are uploaded once per EvalKey object and stay resident (a weak_ptr
+// notices when the host object dies).
 #include <map>
 #include <memory>
 #include <mutex>
@@ -102,18 +103,37 @@ const ofhe_evk* EvkOf(const EvalKey<DCRTPoly>& ek, const HksCtx& h) {
     return g_evk.emplace(ek.get(), e).first->second.evk;
 }
 
-// result polynomials over `params` (EVALUATION) filled from a device slab [n][towers][N]
-std::shared_ptr<std::vector<DCRTPoly>> Download(Op& op, const uint64_t* d, uint32_t n,
-                                                const std::shared_ptr<DCRTPoly::Params>& params) {
+// n device-resident polynomials over `params` (EVALUATION): views [k][towers][N] of ONE slab (they keep it alive)
+std::shared_ptr<std::vector<DCRTPoly>> Views(Op& op, const b200::detail::Slab& slab, uint32_t n,
+                                             const std::shared_ptr<DCRTPoly::Params>& params) {
     auto result = std::make_shared<std::vector<DCRTPoly>>();
     result->reserve(n);
-    const uint32_t towers = (uint32_t)params->GetParams().size();
-    for (uint32_t k = 0; k < n; ++k) {
-        result->emplace_back(params, Format::EVALUATION, true);
-        op.Down(d + (size_t)k * towers * op.N, result->back().GetAllElements(), 0, towers);
-    }
-    op.Sync();
+    const size_t stride = params->GetParams().size() * (size_t)op.N;
+    for (uint32_t k = 0; k < n; ++k)
+        result->push_back(DCRTPoly::FromDevice(params, Format::EVALUATION,
+                                               b200::detail::Slab(slab, slab.get() + k * stride)));
     return result;
+}
+// the digits as one device array [nd][sizeQlP][N]: in place when they are the views EvalKeySwitchPrecomputeCore made
+// (the usual case), gathered into scratch otherwise
+const uint64_t* DigitArray(Op& op, const std::vector<DCRTPoly>& digits, uint32_t sizeQlP,
+                           std::vector<b200::detail::Slab>& keep) {
+    const size_t E = (size_t)sizeQlP * op.N;
+    keep.clear();
+    for (const auto& d : digits) {
+        if (d.GetNumOfElements() != sizeQlP)
+            OPENFHE_THROW("b200 backend: digit with an unexpected number of towers");
+        keep.push_back(d.DeviceSlab());
+    }
+    bool contiguous = true;
+    for (size_t j = 1; j < keep.size(); ++j)
+        contiguous = contiguous && keep[j].get() == keep[0].get() + j * E;
+    if (contiguous)
+        return keep[0].get();
+    uint64_t* dig = op.Scratch(1, digits.size() * (size_t)sizeQlP);
+    for (size_t j = 0; j < keep.size(); ++j)
+        op.Copy(dig + j * E, keep[j].get(), sizeQlP);
+    return dig;
 }
 
 PlaintextModulus NoiseScaleT(const std::shared_ptr<CryptoParametersRNS>& cp) {
@@ -131,12 +151,12 @@ std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::EvalKeySwitchPrecomputeC
     const uint32_t nd      = ofhe_hks_num_digits(h.hks, sizeQl);
     const auto paramsQlP   = c.GetExtendedCRTBasis(cp->GetParamsP());
     Op op(h.N);
-    uint64_t* cd  = op.Slab(0, sizeQl);
-    uint64_t* dig = op.Slab(1, (size_t)nd * (sizeQl + h.sizeP));
-    op.Up(cd, c.GetAllElements(), 0, sizeQl);
-    Check(ofhe_hks_modup(h.hks, sizeQl, cd, dig, op.l.stream), "ofhe_hks_modup");
+    const auto cd = c.DeviceSlab();
+    auto dig      = op.New((size_t)nd * (sizeQl + h.sizeP));
+    Check(ofhe_hks_modup(h.hks, sizeQl, cd.get(), dig.get(), op.l.stream), "ofhe_hks_modup");
+    op.Sync();
     op.rt.n.modup += nd;
-    return Download(op, dig, nd, paramsQlP);
+    return Views(op, dig, nd, paramsQlP);
 }
 
 std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::EvalFastKeySwitchCoreExt(
@@ -149,12 +169,13 @@ std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::EvalFastKeySwitchCoreExt
     const uint32_t nd      = (uint32_t)digits->size();
     const auto paramsQlP   = (*digits)[0].GetParams();
     Op op(h.N);
-    uint64_t* dig = op.Slab(1, (size_t)nd * sizeQlP);
-    uint64_t* e01 = op.Slab(2, (size_t)2 * sizeQlP);
-    for (uint32_t j = 0; j < nd; ++j)
-        op.Up(dig + (size_t)j * sizeQlP * h.N, (*digits)[j].GetAllElements(), 0, sizeQlP);
-    Check(ofhe_hks_inner_product(h.hks, sizeQl, dig, EvkOf(evalKey, h), e01, op.l.stream), "ofhe_hks_inner_product");
-    return Download(op, e01, 2, paramsQlP);
+    std::vector<b200::detail::Slab> keep;
+    const uint64_t* dig = DigitArray(op, *digits, sizeQlP, keep);
+    auto e01            = op.New((size_t)2 * sizeQlP);
+    (void)nd;
+    Check(ofhe_hks_inner_product(h.hks, sizeQl, dig, EvkOf(evalKey, h), e01.get(), op.l.stream), "ofhe_hks_inner_product");
+    op.Sync();
+    return Views(op, e01, 2, paramsQlP);
 }
 
 std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::EvalFastKeySwitchCore(
@@ -177,15 +198,16 @@ std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::EvalFastKeySwitchCore(
     const uint32_t sizeQlP = sizeQl + h.sizeP;
     const uint32_t nd      = (uint32_t)digits->size();
     Op op(h.N);
-    uint64_t* out = op.Slab(0, (size_t)2 * sizeQl);
-    uint64_t* dig = op.Slab(1, (size_t)nd * sizeQlP);
-    uint64_t* e01 = op.Slab(2, (size_t)2 * sizeQlP);
-    for (uint32_t j = 0; j < nd; ++j)
-        op.Up(dig + (size_t)j * sizeQlP * h.N, (*digits)[j].GetAllElements(), 0, sizeQlP);
+    std::vector<b200::detail::Slab> keep;
+    const uint64_t* dig = DigitArray(op, *digits, sizeQlP, keep);
+    uint64_t* e01       = op.Scratch(2, (size_t)2 * sizeQlP);
+    auto out            = op.New((size_t)2 * sizeQl);
+    (void)nd;
     Check(ofhe_hks_inner_product(h.hks, sizeQl, dig, EvkOf(evalKey, h), e01, op.l.stream), "ofhe_hks_inner_product");
-    Check(ofhe_hks_approx_mod_down(h.hks, sizeQl, e01, out, 2, op.l.stream), "ofhe_hks_approx_mod_down");
+    Check(ofhe_hks_approx_mod_down(h.hks, sizeQl, e01, out.get(), 2, op.l.stream), "ofhe_hks_approx_mod_down");
+    op.Sync();
     op.rt.n.moddown += 2;
-    return Download(op, out, 2, paramsQl);
+    return Views(op, out, 2, paramsQl);
 }
 
 std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::KeySwitchCore(const DCRTPoly& a,
@@ -199,13 +221,14 @@ std::shared_ptr<std::vector<DCRTPoly>> KeySwitchHYBRID::KeySwitchCore(const DCRT
     const HksCtx& h       = HksOf(cp);
     const uint32_t sizeQl = a.GetNumOfElements();
     Op op(h.N);
-    uint64_t* ad  = op.Slab(0, sizeQl);
-    uint64_t* out = op.Slab(3, (size_t)2 * sizeQl);
-    op.Up(ad, a.GetAllElements(), 0, sizeQl);
-    Check(ofhe_hks_keyswitch_core(h.hks, sizeQl, ad, EvkOf(evalKey, h), out, op.l.stream), "ofhe_hks_keyswitch_core");
+    const auto ad = a.DeviceSlab();
+    auto out      = op.New((size_t)2 * sizeQl);
+    Check(ofhe_hks_keyswitch_core(h.hks, sizeQl, ad.get(), EvkOf(evalKey, h), out.get(), op.l.stream),
+          "ofhe_hks_keyswitch_core");
+    op.Sync();
     op.rt.n.modup += ofhe_hks_num_digits(h.hks, sizeQl);
     op.rt.n.moddown += 2;
-    return Download(op, out, 2, a.GetParams());
+    return Views(op, out, 2, a.GetParams());
 }
 
 }  // namespace lbcrypto

@@ -105,6 +105,40 @@ public:
         }
         return l.slab[which];
     }
+    // ---- device slabs of resident polynomials: size-keyed free lists (a polynomial's slab is released when its last
+    // owner dies; every device method synchronises its stream before it returns, so a released slab has no work in
+    // flight and can be handed to any thread).  Slabs are IMMUTABLE once published to a polynomial: copies share them.
+    std::shared_ptr<uint64_t> Alloc(size_t words) {
+        uint64_t* p = nullptr;
+        {
+            std::lock_guard<std::mutex> g(pool_mu_);
+            auto it = pool_.find(words);
+            if (it != pool_.end() && !it->second.empty()) {
+                p = it->second.back();
+                it->second.pop_back();
+                pooled_words_ -= words;
+            }
+        }
+        if (!p) {
+            void* v = nullptr;
+            Check(ofhe_malloc(ctx, words * sizeof(uint64_t), &v), "ofhe_malloc");
+            p = static_cast<uint64_t*>(v);
+        }
+        return std::shared_ptr<uint64_t>(p, [this, words](uint64_t* q) {
+            std::lock_guard<std::mutex> g(pool_mu_);
+            if (pooled_words_ + words > kPoolCapWords) {
+                ofhe_free(ctx, q);  // keep the cache bounded (24 GiB)
+                return;
+            }
+            pool_[words].push_back(q);
+            pooled_words_ += words;
+        });
+    }
+    // one of 256 mutexes by object address: const accessors of a polynomial may be called from several threads
+    std::mutex& Stripe(const void* obj) {
+        return stripes_[(reinterpret_cast<uintptr_t>(obj) >> 6) & 255u];
+    }
+
     // process-wide tallies of the device work issued through this backend; OFHE_B200_HAL_STATS=1 prints them at exit
     // (the GPU tests read that line to prove the reference's suites ran on the device path, not on the mirror)
     Counters n;
@@ -127,6 +161,11 @@ private:
                          (unsigned long long)n.bconv, (unsigned long long)n.rescale, (unsigned long long)n.modup,
                          (unsigned long long)n.moddown, (unsigned long long)n.h2d_bytes, (unsigned long long)n.d2h_bytes);
     }
+    static constexpr size_t kPoolCapWords = (size_t)3 << 30;  // 24 GiB of cached slabs
+    std::mutex pool_mu_;
+    std::map<size_t, std::vector<uint64_t*>> pool_;
+    size_t pooled_words_ = 0;
+    std::mutex stripes_[256];
     std::mutex mu_;
     std::map<std::string, ofhe_ring*> rings_;
     std::map<std::string, ofhe_bconv*> bconvs_;

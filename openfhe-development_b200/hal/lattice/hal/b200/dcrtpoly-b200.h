@@ -12,18 +12,22 @@
 //     (a9), AutomorphismTransform in EVALUATION (a15), ApproxSwitchCRTBasis (a10), ApproxModUp (a16's core),
 //     ApproxModDown incl. the BGV t-branches (a11), DropLastElementAndScale (a14), ModReduce (f4), exact
 //     SwitchCRTBasis / ExpandCRTBasis / FastExpandCRTBasisPloverQ (a12), ScaleAndRound DCRT->DCRT (a13).
-//   * host mirror: the polynomial's towers live in an object of the reference's default implementation
-//     (lattice/hal/default/dcrtpoly.h, class DCRTPolyImpl), which also serves everything that is NOT on the hot path
-//     (samplers, CRT interpolation, decryption rounding, BEHZ, serialisation, tower accessors) exactly as the
-//     reference does.  The host code reads and writes towers through GetAllElements()/GetElementAtIndex() all over
-//     src/pke, so the mirror is authoritative and every device method is
-//     upload -> kernels on the calling thread's stream -> download.  (Residency across calls is what the fused
-//     entry points of the C ABI are for -- ofhe_ckks_evalmult, ofhe_hks_keyswitch_core, ... -- see INTEGRATION.md.)
+//   * residency: a polynomial is a device slab [towers x N] (immutable once published, shared by copies, recycled
+//     through a pool) AND / OR a host mirror -- an object of the reference's default implementation
+//     (lattice/hal/default/dcrtpoly.h, class DCRTPolyImpl).  Device methods read their operands' slabs (uploading a
+//     host-only operand once) and leave the result ON THE DEVICE; the mirror of such a result holds parameters and
+//     formats only.  The host code reads and writes towers through GetAllElements() / GetElementAtIndex() /
+//     SetElementAtIndex() all over src/pke: the const accessors download the slab on first use
+//     (thread-safe, once), the non-const ones additionally invalidate it.  Everything that is NOT on the hot path
+//     (samplers, CRT interpolation, decryption rounding, serialisation, arbitrary cyclotomics) is served by the mirror
+//     exactly as the reference computes it.  Chains of device methods -- EvalMult, rescale, rotations, the BSGS loops of
+//     bootstrapping -- therefore never cross PCIe.
 //   * the mirror is never used to COMPUTE a device-listed method: there is no CPU fallback; without a CUDA device the
 //     runtime's constructor throws.
 #ifndef LBCRYPTO_INC_LATTICE_HAL_B200_DCRTPOLY_B200_H
 #define LBCRYPTO_INC_LATTICE_HAL_B200_DCRTPOLY_B200_H
 
+#include <atomic>
 #include <functional>
 #include <memory>
 #include <string>
@@ -57,8 +61,10 @@ public:
 
     // ---- construction / assignment: as lattice/hal/default/dcrtpoly.h:71-127 ---------------------------------
     DCRTPolyB200() = default;
-    DCRTPolyB200(const DCRTPolyType& e) : m_h(e.m_h) {}
-    DCRTPolyB200(DCRTPolyType&& e) noexcept : m_h(std::move(e.m_h)) {}
+    DCRTPolyB200(const DCRTPolyType& e) {
+        CopyFrom(e);
+    }
+    DCRTPolyB200(DCRTPolyType&& e) noexcept : m_h(std::move(e.m_h)), m_d(std::move(e.m_d)), m_w(e.m_w.load()) {}
     DCRTPolyB200(const Host& h) : m_h(h) {}              // NOLINT: the mirror type converts freely
     DCRTPolyB200(Host&& h) noexcept : m_h(std::move(h)) {}  // NOLINT
     DCRTPolyB200(const PolyLargeType& e, const std::shared_ptr<Params>& params) : m_h(e, params) {}
@@ -74,39 +80,42 @@ public:
     DCRTPolyB200(DugType& dug, const std::shared_ptr<Params>& p, Format f = Format::EVALUATION) : m_h(dug, p, f) {}
 
     DCRTPolyType& operator=(const DCRTPolyType& rhs) noexcept override {
-        m_h = rhs.m_h;
+        if (this != &rhs)
+            CopyFrom(rhs);
         return *this;
     }
     DCRTPolyType& operator=(DCRTPolyType&& rhs) noexcept override {
         m_h = std::move(rhs.m_h);
+        m_d = std::move(rhs.m_d);
+        m_w = rhs.m_w.load();
         return *this;
     }
     DCRTPolyType& operator=(const PolyLargeType& rhs) noexcept {
-        m_h = rhs;
+        HW() = rhs;
         return *this;
     }
     DCRTPolyType& operator=(const PolyType& rhs) noexcept {
-        m_h = rhs;
+        HW() = rhs;
         return *this;
     }
     DCRTPolyType& operator=(std::initializer_list<uint64_t> rhs) noexcept override {
-        m_h = rhs;
+        HW() = rhs;
         return *this;
     }
     DCRTPolyType& operator=(uint64_t val) noexcept {
-        m_h = val;
+        HW() = val;
         return *this;
     }
     DCRTPolyType& operator=(const std::vector<int64_t>& rhs) noexcept {
-        m_h = rhs;
+        HW() = rhs;
         return *this;
     }
     DCRTPolyType& operator=(const std::vector<int32_t>& rhs) noexcept {
-        m_h = rhs;
+        HW() = rhs;
         return *this;
     }
     DCRTPolyType& operator=(std::initializer_list<std::string> rhs) noexcept {
-        m_h = rhs;
+        HW() = rhs;
         return *this;
     }
 
@@ -120,20 +129,33 @@ public:
     const std::shared_ptr<Params>& GetParams() const {
         return m_h.GetParams();
     }
+    // tower accessors: the const form downloads a device-only polynomial once; the non-const form hands the towers to
+    // the host code for writing, so the device copy is dropped
     const std::vector<PolyType>& GetAllElements() const {
-        return m_h.GetAllElements();
+        return H().GetAllElements();
     }
     std::vector<PolyType>& GetAllElements() {
-        return m_h.GetAllElements();
+        return HW().GetAllElements();
     }
     void SetElementAtIndex(usint index, const PolyType& element) {
-        m_h.SetElementAtIndex(index, element);
+        HW().SetElementAtIndex(index, element);
     }
     void SetElementAtIndex(usint index, PolyType&& element) {
-        m_h.SetElementAtIndex(index, std::move(element));
+        HW().SetElementAtIndex(index, std::move(element));
+    }
+    // metadata only: never moves data (the interface's version goes through GetAllElements())
+    usint GetNumOfElements() const {
+        return m_h.GetAllElements().size();
     }
     const Host& HostMirror() const {
-        return m_h;
+        return H();
+    }
+    // the towers as PARAMETER carriers (moduli, roots, formats): valid without any data movement
+    const std::vector<PolyType>& TowerMeta() const {
+        return m_h.GetAllElements();
+    }
+    bool OnDevice() const {
+        return (m_w.load() & kDev) != 0;
     }
     static const std::string GetElementName() {
         return "DCRTPolyImpl";
@@ -146,96 +168,96 @@ public:
     }
     template <class Archive>
     void save(Archive& ar, std::uint32_t const version) const {
-        m_h.save(ar, version);  // byte-identical archives: the same three fields in the same order (dcrtpoly.h:337-341)
+        H().save(ar, version);  // byte-identical archives: the same three fields in the same order (dcrtpoly.h:337-341)
     }
     template <class Archive>
     void load(Archive& ar, std::uint32_t const version) {
-        m_h.load(ar, version);
+        HW().load(ar, version);
     }
 
     // ---- not on the hot path: served by the mirror exactly as the reference does ---------------------------------
     DCRTPolyType CloneWithNoise(const DiscreteGaussianGeneratorImpl<VecType>& dgg, Format format) const override {
-        return m_h.CloneWithNoise(dgg, format);
+        return H().CloneWithNoise(dgg, format);
     }
     DCRTPolyType CloneTowers(uint32_t startTower, uint32_t endTower) const {
-        return m_h.CloneTowers(startTower, endTower);
+        return H().CloneTowers(startTower, endTower);
     }
     bool operator==(const DCRTPolyType& rhs) const override {
-        return m_h == rhs.m_h;
+        return H() == rhs.H();
     }
     DCRTPolyType& operator+=(const Integer& rhs) override {
-        m_h += rhs;
+        HW() += rhs;
         return *this;
     }
     DCRTPolyType& operator+=(const NativeInteger& rhs) override {
-        m_h += rhs;
+        HW() += rhs;
         return *this;
     }
     DCRTPolyType& operator-=(const Integer& rhs) override {
-        m_h -= rhs;
+        HW() -= rhs;
         return *this;
     }
     DCRTPolyType& operator-=(const NativeInteger& rhs) override {
-        m_h -= rhs;
+        HW() -= rhs;
         return *this;
     }
     DCRTPolyType& operator*=(const Integer& rhs) override {
-        m_h *= rhs;
+        HW() *= rhs;
         return *this;
     }
     DCRTPolyType& operator*=(const NativeInteger& rhs) override {
-        m_h *= rhs;
+        HW() *= rhs;
         return *this;
     }
     std::vector<DCRTPolyType> BaseDecompose(usint baseBits, bool evalModeAnswer) const override {
-        return Wrap(m_h.BaseDecompose(baseBits, evalModeAnswer));
+        return Wrap(H().BaseDecompose(baseBits, evalModeAnswer));
     }
     std::vector<DCRTPolyType> PowersOfBase(usint baseBits) const override {
-        return Wrap(m_h.PowersOfBase(baseBits));
+        return Wrap(H().PowersOfBase(baseBits));
     }
     std::vector<DCRTPolyType> CRTDecompose(uint32_t baseBits) const {
-        return Wrap(m_h.CRTDecompose(baseBits));
+        return Wrap(H().CRTDecompose(baseBits));
     }
     DCRTPolyType Plus(const Integer& rhs) const override {
-        return m_h.Plus(rhs);
+        return H().Plus(rhs);
     }
     DCRTPolyType Plus(const std::vector<Integer>& rhs) const {
-        return m_h.Plus(rhs);
+        return H().Plus(rhs);
     }
     DCRTPolyType Minus(const Integer& rhs) const override {
-        return m_h.Minus(rhs);
+        return H().Minus(rhs);
     }
     DCRTPolyType Minus(const std::vector<Integer>& rhs) const {
-        return m_h.Minus(rhs);
+        return H().Minus(rhs);
     }
     DCRTPolyType Times(const Integer& rhs) const override {
-        return m_h.Times(rhs);
+        return H().Times(rhs);
     }
     DCRTPolyType Times(const std::vector<Integer>& rhs) const {
-        return m_h.Times(rhs);
+        return H().Times(rhs);
     }
     DCRTPolyType Times(NativeInteger::SignedNativeInt rhs) const override {
-        return m_h.Times(rhs);
+        return H().Times(rhs);
     }
 #if NATIVEINT != 64
     DCRTPolyType Times(int64_t rhs) const {
-        return m_h.Times(rhs);
+        return H().Times(rhs);
     }
 #endif
     DCRTPolyType MultiplicativeInverse() const override {
-        return m_h.MultiplicativeInverse();
+        return H().MultiplicativeInverse();
     }
     bool InverseExists() const override {
-        return m_h.InverseExists();
+        return H().InverseExists();
     }
     bool IsEmpty() const override {
-        return m_h.IsEmpty();
+        return (m_w.load() & kDev) ? m_h.GetAllElements().empty() : m_h.IsEmpty();
     }
     void SetValuesToZero() override {
-        m_h.SetValuesToZero();
+        HW().SetValuesToZero();
     }
     void AddILElementOne() override {
-        m_h.AddILElementOne();
+        HW().AddILElementOne();
     }
     void DropLastElement() override {
         m_h.DropLastElement();
@@ -244,22 +266,22 @@ public:
         m_h.DropLastElements(i);
     }
     PolyLargeType CRTInterpolate() const override {
-        return m_h.CRTInterpolate();
+        return H().CRTInterpolate();
     }
     PolyType DecryptionCRTInterpolate(PlaintextModulus ptm) const override {
-        return m_h.DecryptionCRTInterpolate(ptm);
+        return H().DecryptionCRTInterpolate(ptm);
     }
     PolyType ToNativePoly() const override {
-        return m_h.ToNativePoly();
+        return H().ToNativePoly();
     }
     PolyLargeType CRTInterpolateIndex(usint i) const override {
-        return m_h.CRTInterpolateIndex(i);
+        return H().CRTInterpolateIndex(i);
     }
     Integer GetWorkingModulus() const override {
         return m_h.GetWorkingModulus();
     }
     void SetValuesModSwitch(const DCRTPolyType& element, const NativeInteger& modulus) override {
-        m_h.SetValuesModSwitch(element.m_h, modulus);
+        HW().SetValuesModSwitch(element.H(), modulus);
     }
     std::shared_ptr<Params> GetExtendedCRTBasis(const std::shared_ptr<Params>& paramsP) const override {
         return m_h.GetExtendedCRTBasis(paramsP);
@@ -267,7 +289,7 @@ public:
     void TimesQovert(const std::shared_ptr<Params>& paramsQ, const std::vector<NativeInteger>& tInvModq,
                      const NativeInteger& t, const NativeInteger& NegQModt,
                      const NativeInteger& NegQModtPrecon) override {
-        m_h.TimesQovert(paramsQ, tInvModq, t, NegQModt, NegQModtPrecon);
+        HW().TimesQovert(paramsQ, tInvModq, t, NegQModt, NegQModtPrecon);
     }
     void ExpandCRTBasisReverseOrder(const std::shared_ptr<Params>& paramsQP, const std::shared_ptr<Params>& paramsP,
                                     const std::vector<NativeInteger>& QHatInvModq,
@@ -276,18 +298,16 @@ public:
                                     const std::vector<std::vector<NativeInteger>>& alphaQModp,
                                     const std::vector<DoubleNativeInt>& modpBarrettMu, const std::vector<double>& qInv,
                                     Format resultFormat) override {
-        m_h.ExpandCRTBasisReverseOrder(paramsQP, paramsP, QHatInvModq, QHatInvModqPrecon, QHatModp, alphaQModp,
+        HW().ExpandCRTBasisReverseOrder(paramsQP, paramsP, QHatInvModq, QHatInvModqPrecon, QHatModp, alphaQModp,
                                        modpBarrettMu, qInv, resultFormat);
     }
-    void ExpandCRTBasisQlHat(const std::shared_ptr<Params>& paramsQ, const std::vector<NativeInteger>& QlHatModq,
-                             const std::vector<NativeInteger>& QlHatModqPrecon, const usint sizeQ) override;
     PolyType ScaleAndRound(const NativeInteger& t, const std::vector<NativeInteger>& tQHatInvModqDivqModt,
                            const std::vector<NativeInteger>& tQHatInvModqDivqModtPrecon,
                            const std::vector<NativeInteger>& tQHatInvModqBDivqModt,
                            const std::vector<NativeInteger>& tQHatInvModqBDivqModtPrecon,
                            const std::vector<double>& tQHatInvModqDivqFrac,
                            const std::vector<double>& tQHatInvModqBDivqFrac) const override {
-        return m_h.ScaleAndRound(t, tQHatInvModqDivqModt, tQHatInvModqDivqModtPrecon, tQHatInvModqBDivqModt,
+        return H().ScaleAndRound(t, tQHatInvModqDivqModt, tQHatInvModqDivqModtPrecon, tQHatInvModqBDivqModt,
                                  tQHatInvModqBDivqModtPrecon, tQHatInvModqDivqFrac, tQHatInvModqBDivqFrac);
     }
     PolyType ScaleAndRound(const std::vector<NativeInteger>& moduliQ, const NativeInteger& t,
@@ -295,46 +315,11 @@ public:
                            const std::vector<NativeInteger>& tgammaQHatModqPrecon,
                            const std::vector<NativeInteger>& negInvqModtgamma,
                            const std::vector<NativeInteger>& negInvqModtgammaPrecon) const override {
-        return m_h.ScaleAndRound(moduliQ, t, tgamma, tgammaQHatModq, tgammaQHatModqPrecon, negInvqModtgamma,
+        return H().ScaleAndRound(moduliQ, t, tgamma, tgammaQHatModq, tgammaQHatModqPrecon, negInvqModtgamma,
                                  negInvqModtgammaPrecon);
     }
-    void FastBaseConvqToBskMontgomery(
-        const std::shared_ptr<Params>& paramsQBsk, const std::vector<NativeInteger>& moduliQ,
-        const std::vector<NativeInteger>& moduliBsk, const std::vector<DoubleNativeInt>& modbskBarrettMu,
-        const std::vector<NativeInteger>& mtildeQHatInvModq, const std::vector<NativeInteger>& mtildeQHatInvModqPrecon,
-        const std::vector<std::vector<NativeInteger>>& QHatModbsk, const std::vector<uint64_t>& QHatModmtilde,
-        const std::vector<NativeInteger>& QModbsk, const std::vector<NativeInteger>& QModbskPrecon,
-        const uint64_t& negQInvModmtilde, const std::vector<NativeInteger>& mtildeInvModbsk,
-        const std::vector<NativeInteger>& mtildeInvModbskPrecon) override {
-        m_h.FastBaseConvqToBskMontgomery(paramsQBsk, moduliQ, moduliBsk, modbskBarrettMu, mtildeQHatInvModq,
-                                         mtildeQHatInvModqPrecon, QHatModbsk, QHatModmtilde, QModbsk, QModbskPrecon,
-                                         negQInvModmtilde, mtildeInvModbsk, mtildeInvModbskPrecon);
-    }
-    void FastRNSFloorq(const NativeInteger& t, const std::vector<NativeInteger>& moduliQ,
-                       const std::vector<NativeInteger>& moduliBsk, const std::vector<DoubleNativeInt>& modbskBarrettMu,
-                       const std::vector<NativeInteger>& tQHatInvModq,
-                       const std::vector<NativeInteger>& tQHatInvModqPrecon,
-                       const std::vector<std::vector<NativeInteger>>& QHatModbsk,
-                       const std::vector<std::vector<NativeInteger>>& qInvModbsk,
-                       const std::vector<NativeInteger>& tQInvModbsk,
-                       const std::vector<NativeInteger>& tQInvModbskPrecon) override {
-        m_h.FastRNSFloorq(t, moduliQ, moduliBsk, modbskBarrettMu, tQHatInvModq, tQHatInvModqPrecon, QHatModbsk,
-                          qInvModbsk, tQInvModbsk, tQInvModbskPrecon);
-    }
-    void FastBaseConvSK(const std::shared_ptr<Params>& paramsQ, const std::vector<DoubleNativeInt>& modqBarrettMu,
-                        const std::vector<NativeInteger>& moduliBsk,
-                        const std::vector<DoubleNativeInt>& modbskBarrettMu,
-                        const std::vector<NativeInteger>& BHatInvModb,
-                        const std::vector<NativeInteger>& BHatInvModbPrecon,
-                        const std::vector<NativeInteger>& BHatModmsk, const NativeInteger& BInvModmsk,
-                        const NativeInteger& BInvModmskPrecon, const std::vector<std::vector<NativeInteger>>& BHatModq,
-                        const std::vector<NativeInteger>& BModq,
-                        const std::vector<NativeInteger>& BModqPrecon) override {
-        m_h.FastBaseConvSK(paramsQ, modqBarrettMu, moduliBsk, modbskBarrettMu, BHatInvModb, BHatInvModbPrecon,
-                           BHatModmsk, BInvModmsk, BInvModmskPrecon, BHatModq, BModq, BModqPrecon);
-    }
     void SwitchModulusAtIndex(size_t index, const Integer& modulus, const Integer& rootOfUnity) override {
-        m_h.SwitchModulusAtIndex(index, modulus, rootOfUnity);
+        HW().SwitchModulusAtIndex(index, modulus, rootOfUnity);
     }
 
     // ---- the hot path: DEVICE (definitions in dcrtpoly-b200-impl.h) -----------------------------------------------
@@ -397,9 +382,70 @@ public:
                                const std::vector<DoubleNativeInt>& modoBarretMu) const override;
     void ScaleAndRoundPOverQ(const std::shared_ptr<Params>& paramsQ,
                              const std::vector<NativeInteger>& pInvModq) override;
+    void ExpandCRTBasisQlHat(const std::shared_ptr<Params>& paramsQ, const std::vector<NativeInteger>& QlHatModq,
+                             const std::vector<NativeInteger>& QlHatModqPrecon, const usint sizeQ) override;
+    // BEHZ BFV (f4): dcrtpoly-impl.h:1694-1921
+    void FastBaseConvqToBskMontgomery(
+        const std::shared_ptr<Params>& paramsQBsk, const std::vector<NativeInteger>& moduliQ,
+        const std::vector<NativeInteger>& moduliBsk, const std::vector<DoubleNativeInt>& modbskBarrettMu,
+        const std::vector<NativeInteger>& mtildeQHatInvModq, const std::vector<NativeInteger>& mtildeQHatInvModqPrecon,
+        const std::vector<std::vector<NativeInteger>>& QHatModbsk, const std::vector<uint64_t>& QHatModmtilde,
+        const std::vector<NativeInteger>& QModbsk, const std::vector<NativeInteger>& QModbskPrecon,
+        const uint64_t& negQInvModmtilde, const std::vector<NativeInteger>& mtildeInvModbsk,
+        const std::vector<NativeInteger>& mtildeInvModbskPrecon) override;
+    void FastRNSFloorq(const NativeInteger& t, const std::vector<NativeInteger>& moduliQ,
+                       const std::vector<NativeInteger>& moduliBsk, const std::vector<DoubleNativeInt>& modbskBarrettMu,
+                       const std::vector<NativeInteger>& tQHatInvModq,
+                       const std::vector<NativeInteger>& tQHatInvModqPrecon,
+                       const std::vector<std::vector<NativeInteger>>& QHatModbsk,
+                       const std::vector<std::vector<NativeInteger>>& qInvModbsk,
+                       const std::vector<NativeInteger>& tQInvModbsk,
+                       const std::vector<NativeInteger>& tQInvModbskPrecon) override;
+    void FastBaseConvSK(const std::shared_ptr<Params>& paramsQ, const std::vector<DoubleNativeInt>& modqBarrettMu,
+                        const std::vector<NativeInteger>& moduliBsk,
+                        const std::vector<DoubleNativeInt>& modbskBarrettMu,
+                        const std::vector<NativeInteger>& BHatInvModb,
+                        const std::vector<NativeInteger>& BHatInvModbPrecon,
+                        const std::vector<NativeInteger>& BHatModmsk, const NativeInteger& BInvModmsk,
+                        const NativeInteger& BInvModmskPrecon, const std::vector<std::vector<NativeInteger>>& BHatModq,
+                        const std::vector<NativeInteger>& BModq,
+                        const std::vector<NativeInteger>& BModqPrecon) override;
+
+    // ---- residency plumbing (public for the rebound KeySwitchHYBRID, hal/keyswitch-hybrid-b200.cpp) ---------------
+    // device slab of this polynomial [GetNumOfElements()][N] (uploads a host-only polynomial once)
+    std::shared_ptr<uint64_t> DeviceSlab() const;
+    // a device-resident polynomial over (params, format) whose rows are `slab` (EVALUATION / COEFFICIENT as stated)
+    static DCRTPolyType FromDevice(const std::shared_ptr<Params>& params, Format format, std::shared_ptr<uint64_t> slab);
 
 private:
-    Host m_h;
+    static constexpr uint8_t kHost = 1, kDev = 2;
+    mutable Host m_h;                      // towers (values valid iff m_w & kHost), parameters and formats (always valid)
+    mutable std::shared_ptr<uint64_t> m_d;  // device rows (valid iff m_w & kDev); immutable once published
+    mutable std::atomic<uint8_t> m_w{kHost};
+
+    void EnsureHost() const;  // download once, thread-safe
+    const Host& H() const {
+        if (!(m_w.load(std::memory_order_acquire) & kHost))
+            EnsureHost();
+        return m_h;
+    }
+    Host& HW() {  // the host code is about to write the towers: the device copy dies
+        if (!(m_w.load(std::memory_order_acquire) & kHost))
+            EnsureHost();
+        m_d.reset();
+        m_w.store(kHost, std::memory_order_release);
+        return m_h;
+    }
+    void CopyFrom(const DCRTPolyType& e);
+    // this polynomial becomes the device-resident (params, format, slab); towers carry parameters and formats only
+    void Adopt(Host&& meta, std::shared_ptr<uint64_t> slab) {
+        m_h = std::move(meta);
+        m_d = std::move(slab);
+        m_w.store(kDev, std::memory_order_release);
+    }
+    static Host Meta(const std::shared_ptr<Params>& params, Format format) {
+        return Host(params, format, false);
+    }
 
     static std::vector<DCRTPolyType> Wrap(std::vector<Host>&& v) {
         std::vector<DCRTPolyType> r;

@@ -30,6 +30,7 @@ SIGNATURES = {
     "ofhe_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ofhe_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ofhe_memcpy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "ofhe_memset0": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "ofhe_stream_sync": (C.c_int, [_vp, _vp]),
     "ofhe_stream_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "ofhe_stream_destroy": (C.c_int, [_vp, _vp]),
@@ -40,6 +41,9 @@ SIGNATURES = {
     "ofhe_ntt_inv": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, _vp]),
     "ofhe_ew_binop": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
     "ofhe_ew_mul_scalars": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "ofhe_behz_mtilde": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp]),
+    "ofhe_behz_mtilde_fix": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_behz_sk_fix": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _vp, _vp]),
     "ofhe_switch_modulus": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "ofhe_automorphism": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "ofhe_automorphism_coeff": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp]),

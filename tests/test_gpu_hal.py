@@ -88,3 +88,24 @@ def test_general_she():
 def test_ckksrns_automorphism():
     """UTCKKSRNS_AUTOMORPHISM (UnitTestCKKSrnsAutomorphism.cpp)"""
     run_suite("pke_tests_b200", "*UTCKKSRNS_AUTOMORPHISM*", 600, ["limb_ntt", "automorph_limbs", "moddown"])
+
+
+def test_bgvrns_bfvrns_serialization():
+    """UTBGVRNS_SER / UTBFVRNS_SER (UnitTestBGVrnsSerialize.cpp, UnitTestBFVrnsSerialize.cpp)"""
+    run_suite("pke_tests_b200", "*UTBGVRNS_SER*:UTBFVRNS_SER*", 900, ["limb_ntt"])
+
+
+def test_bootstrap_driver_config4_parameters_small_ring():
+    """tools/hal_bootstrap.cpp (BASELINE config 4's parameters: simple-ckks-bootstrapping.cpp:63-156) at N = 2^12 on the
+    device path: the bootstrapped ciphertext decrypts to the input within the scheme's precision."""
+    import json
+
+    exe = os.path.join(HAL, "bootstrap_b200")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built")
+    env = dict(os.environ, OFHE_B200_HAL_STATS="1", OMP_NUM_THREADS="8")
+    p = subprocess.run([exe, "--logn", "12", "--slots", "8"], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["precision_bits"] > 12 and line["levels_remaining_after"] >= 9, line
+    assert "device work" in p.stderr and "moddown=0 " not in p.stderr, p.stderr[-500:]
