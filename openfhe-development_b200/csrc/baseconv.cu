@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) bconv_wide_kernel(RingDev r, BConvDe
 }  // namespace
 
 BConv::~BConv() {
-    for (void* p : {(void*)qhatinv_d, (void*)mat_d, (void*)dbl_d, (void*)alpha_d, (void*)extra_d})
+    for (void* p : {(void*)qhatinv_d, (void*)mat_d, (void*)dbl_d, (void*)alpha_d, (void*)extra_d, (void*)tc_bmat_d, (void*)tc_desc_d})
         if (p)
             cudaFree(p);
 }
@@ -308,6 +308,11 @@ void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* o
                   size_t out_stride, bool premultiplied, cudaStream_t st) {
     if (t.sizeP == 0 || t.sizeQ == 0 || batch == 0)
         return;
+    if (bconv_tc_eligible(r, t)) {  // dense integer contraction on tcgen05 (baseconv_tc.cu)
+        const BConvJob job{&t, in, out, batch, in_stride, out_stride};
+        launch_bconv_tc(r, &job, 1, premultiplied, st);
+        return;
+    }
     BConvDev d{t.sizeQ, t.sizeP, t.qhatinv_d, reinterpret_cast<const uint2*>(t.mat_d), t.mode, t.dbl_d, t.alpha_d, t.extra_d};
     if (t.sizeQ > 64) {
         dim3 g((r.N + kThreads - 1) / kThreads, t.sizeP, batch);

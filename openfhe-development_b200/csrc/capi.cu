@@ -385,6 +385,7 @@ static std::unique_ptr<BConv> bconv_from_tables(const Ring& r, uint32_t n_src, c
     t->pmap = make_map(dst, n_dst);
     upload((void**)&t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size());
     upload((void**)&t->mat_d, mat.data(), sizeof(uint32_t) * mat.size());
+    bconv_finalize(r, *t);
     return t;
 }
 
@@ -1197,6 +1198,7 @@ std::unique_ptr<BConv> build_bconv(const Ring& r, uint32_t n_src, const uint32_t
     OFHE_CUDA(cudaMalloc(&t->mat_d, sizeof(uint32_t) * mat.size()));
     h2d_blocking(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size());
     h2d_blocking(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size());
+    bconv_finalize(r, *t);
     return t;
 }
 }  // namespace

@@ -60,6 +60,7 @@ std::unique_ptr<BConv> make_bconv(const Ring& r, const std::vector<uint32_t>& sr
     OFHE_CUDA(cudaMalloc(&t->mat_d, sizeof(uint32_t) * mat.size()));
     h2d_blocking(t->qhatinv_d, hinv.data(), sizeof(uint64_t) * hinv.size());
     h2d_blocking(t->mat_d, mat.data(), sizeof(uint32_t) * mat.size());
+    bconv_finalize(r, *t);
     return t;
 }
 
@@ -232,11 +233,22 @@ void Hks::modup(uint32_t sizeQl, const uint64_t* c, uint64_t* digits, uint64_t* 
     const size_t N = r.N, sizeQlP = sizeQl + sizeP;
     // 1. all digits at once: coefficient-format copy of c                            (keyswitch-hybrid.cpp:359)
     launch_ntt_inv(r, c, coeff_tmp, lv.map_Ql, st, nullptr, lv.fold_modup_d);  // y_i = INTT(c)_i * QHatInv_i
+    // 2. fast base conversion straight into the complementary rows of D_j               (:360-365): every digit in
+    //    ONE tensor-core launch when the digits qualify (<= 16 limbs each), else one CUDA-core launch per digit
+    bool all_tc = lv.n_digits <= 4;
+    for (uint32_t j = 0; j < lv.n_digits && all_tc; ++j)
+        all_tc = bconv_tc_eligible(r, *lv.modup[j]);
+    if (all_tc) {
+        BConvJob jobs[4];
+        for (uint32_t j = 0; j < lv.n_digits; ++j)
+            jobs[j] = BConvJob{lv.modup[j].get(), coeff_tmp, digits + (size_t)j * sizeQlP * N, 1, 0, 0};
+        launch_bconv_tc(r, jobs, lv.n_digits, /*premultiplied=*/true, st);
+    }
     for (uint32_t j = 0; j < lv.n_digits; ++j) {
         uint64_t* D      = digits + (size_t)j * sizeQlP * N;
         const uint32_t s = j * alpha, ds = std::min(alpha, sizeQl - s);
-        // 2. fast base conversion straight into the complementary rows of D_j           (:360-365)
-        launch_bconv(r, *lv.modup[j], coeff_tmp, D, 1, 0, 0, /*premultiplied=*/true, st);
+        if (!all_tc)
+            launch_bconv(r, *lv.modup[j], coeff_tmp, D, 1, 0, 0, /*premultiplied=*/true, st);
         // 3. the digit's own rows keep the ORIGINAL evaluation-format limbs of c          (:372-373); inside the fused
         //    key switch the inner product reads them from c directly and the copies are skipped
         if (own_rows)

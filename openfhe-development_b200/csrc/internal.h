@@ -184,8 +184,31 @@ struct BConv {
     uint64_t* alpha_d = nullptr;     // [sizeQ+1][sizeP]
     uint64_t* extra_d = nullptr;     // [sizeP]
     PosMap xomap;
+    // tensor-core path (baseconv_tc.cu): byte-digit image of the matrix in the MMA's shared-memory layout and the
+    // device-resident description of the conversion; built by bconv_finalize() for <= 16 source limbs
+    uint8_t* tc_bmat_d = nullptr;
+    struct BConvTcDesc* tc_desc_d = nullptr;
     ~BConv();
 };
+struct BConvTcDesc {
+    uint32_t sizeQ, sizeP;
+    const uint8_t* bmat;      // [ceil(sizeP / 16)][256 rows][128 bytes], 128-byte swizzle
+    const uint64_t* qhatinv;  // [sizeQ][2]
+    uint16_t qidx[16], qpos[16];
+    uint16_t pidx[kMaxLimbs], ppos[kMaxLimbs];
+};
+// called once by whoever fills a BConv (after mat_d / qhatinv_d / the maps are in place)
+void bconv_finalize(const Ring& r, BConv& t);
+bool bconv_tc_eligible(const Ring& r, const BConv& t);
+// several approximate conversions (mode 0, <= 16 source limbs each) as ONE persistent tensor-core launch
+struct BConvJob {
+    const BConv* t;
+    const uint64_t* in;
+    uint64_t* out;
+    uint32_t batch;
+    size_t in_stride, out_stride;
+};
+void launch_bconv_tc(const Ring& r, const BConvJob* jobs, uint32_t njobs, bool premultiplied, cudaStream_t st);
 // `batch` independent polynomials, `in_stride` / `out_stride` words apart
 // premultiplied: the source residues already carry the factor QHatInvModq (folded into the preceding inverse NTT)
 void launch_bconv(const Ring& r, const BConv& t, const uint64_t* in, uint64_t* out, uint32_t batch, size_t in_stride,
