@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) bconv_wide_kernel(RingDev r, BConvDe
 }  // namespace
 
 BConv::~BConv() {
-    for (void* p : {(void*)qhatinv_d, (void*)mat_d, (void*)dbl_d, (void*)alpha_d, (void*)extra_d, (void*)tc_bmat_d, (void*)tc_desc_d})
+    for (void* p : {(void*)qhatinv_d, (void*)mat_d, (void*)dbl_d, (void*)alpha_d, (void*)extra_d, (void*)tc_bmat_d, (void*)tc_dst_tab_d, (void*)tc_desc_d})
         if (p)
             cudaFree(p);
 }

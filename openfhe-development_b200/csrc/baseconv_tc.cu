@@ -26,13 +26,15 @@
 //
 // Eligibility: mode 0 (approximate conversion), <= 16 source limbs, N >= 128.  Everything else stays on baseconv.cu.
 #include <cstdlib>
+#include <vector>
 
 #include "internal.h"
 
 namespace ofhe {
 namespace {
 
-constexpr int kTcThreads  = 512;
+constexpr int kEpiThreads = 512;                  // 16 transpose / epilogue warps
+constexpr int kTcThreads  = kEpiThreads + 32;     // + the MMA warp
 constexpr int kTileM      = 128;                  // coefficients per tile = TMEM lanes
 constexpr int kChunkOut   = 16;                   // target limbs per accumulator buffer
 constexpr int kChunkN     = 256;                  // columns per buffer: 16 limbs x 16 digit weights
@@ -41,7 +43,7 @@ constexpr int kChunkBytes = kChunkN * kK;         // 32 KiB of B per chunk
 constexpr int kTileBytes  = kTileM * kK;          // 16 KiB of A per tile
 constexpr int kMaxChunks  = 5;                    // 80 target limbs per job (larger conversions are split into jobs)
 constexpr int kMaxJobs    = 4;
-constexpr int kSub        = kTcThreads / 128;     // warps per TMEM lane quarter
+constexpr int kSub        = kEpiThreads / 128;     // warps per TMEM lane quarter
 constexpr int kOutPerThr  = kChunkOut / kSub;     // outputs of a chunk per thread
 
 struct TcJob {
@@ -68,19 +70,30 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// hardware-suspended try_wait (10 ms hint); a completion that never comes (a bug) traps after a few seconds instead
+// of hanging the device
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 24))
-            __trap();  // a lost MMA completion must fail loudly, never hang the device
+        if (!done && spin > 400)
+            __trap();
     }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// global -> shared 1-D bulk copy (TMA), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -109,7 +122,7 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 32 consecutive columns of this thread's TMEM lane
+// 32 consecutive columns (two outputs' digit-weight sums) of this thread's TMEM lane; completion via tmem_wait32
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -121,7 +134,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    // the wait is tied to the registers so that no use of them can be scheduled above it
+}
+// tcgen05.wait::ld covers every load of the thread issued so far; it is tied to the registers it releases so that
+// no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait32(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
@@ -129,6 +145,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // S = sum_{c < 15} v[c] 2^(8c) (every v[c] < 2^23) reduced mod p: the value of BarrettUint128ModUint64 on the
@@ -145,82 +164,121 @@ __device__ __forceinline__ uint64_t fold_columns(const uint32_t* v, uint64_t p, 
     return barrett128((uint64_t)(s >> 64), (uint64_t)s, p, mu_hi, mu_lo);
 }
 
+#ifndef OFHE_TC_FASTRED
+#define OFHE_TC_FASTRED 1
+#endif
+#ifndef OFHE_TC_DB
+#define OFHE_TC_DB 0  // 1: the second output pair's TMEM load in flight during the first pair's reduction (64 live registers)
+#endif
+// The same residue with about half the multiplier work, for moduli of at least 32 bits: the two upper 32-bit words of
+// S are folded down with c2 = 2^64 mod p and c3 = 2^96 mod p (two 32 x 60-bit products each),
+//     T = (s1:s0) + s2 c2 + s3 c3  <  2^94,   T = S (mod p),
+// and T takes the single-word Barrett step of modarith.cuh (quotient estimate within 2 for T < 2^(63+k), k >= 31).
+__device__ __forceinline__ uint64_t fold_columns_fast(const uint32_t* v, uint64_t p, uint64_t mu, uint32_t k, uint64_t c2,
+                                                      uint64_t c3) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+        e[i] = v[2 * i] + (v[2 * i + 1] << 8);
+    e[7] = v[14];
+    const uint64_t a_lo = (uint64_t)e[0] | ((uint64_t)e[2] << 32), a_hi = (uint64_t)e[4] | ((uint64_t)e[6] << 32);
+    const uint64_t b_lo = (uint64_t)e[1] | ((uint64_t)e[3] << 32), b_hi = (uint64_t)e[5] | ((uint64_t)e[7] << 32);
+    const unsigned __int128 s = (((unsigned __int128)a_hi << 64) | a_lo) + ((((unsigned __int128)b_hi << 64) | b_lo) << 16);
+    const uint64_t s_hi = (uint64_t)(s >> 64);
+    const uint32_t s2 = (uint32_t)s_hi, s3 = (uint32_t)(s_hi >> 32);
+    const uint64_t lo_part = (uint64_t)s2 * (uint32_t)c2;                                            // < 2^64
+    const uint64_t lo_par2 = (uint64_t)s3 * (uint32_t)c3;
+    const uint64_t hi_part = (uint64_t)s2 * (uint32_t)(c2 >> 32) + (uint64_t)s3 * (uint32_t)(c3 >> 32);  // < 2^61
+    const unsigned __int128 t = (unsigned __int128)(uint64_t)s + lo_part + lo_par2 + ((unsigned __int128)hi_part << 32);
+    return barrett_reduce_prod((uint64_t)(t >> 64), (uint64_t)t, p, mu, k);
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------
 // dynamic shared memory (1024-byte aligned by hand): B image [kMaxChunks][32 KiB] | A tiles [2][16 KiB] | tables
 struct TcTables {
-    uint64_t dst[kMaxChunks * kChunkOut][4];  // p, mu128_hi, mu128_lo, output row
-    uint64_t src[16][4];                      // q, QHatInv, Shoup(QHatInv), input row (or ~0 for padding)
-    uint64_t bar[2];
+    uint64_t dst[kMaxChunks * kChunkOut][8];  // p, mu128_hi, mu128_lo, word offset of the output row, mu, k, c2, c3
+    uint64_t src[16][4];                      // q, QHatInv, Shoup(QHatInv), word offset of the input row (~0: padding)
+    uint64_t full[2];                         // accumulator buffer written   (1 arrival: tcgen05.commit)
+    uint64_t empty[2];                        // accumulator buffer drained   (16 arrivals: one per epilogue warp)
+    uint64_t afull[2];                        // A tile staged                (16 arrivals)
+    uint64_t job;                             // tables + B image of a job landed (bulk copies, byte count)
     uint32_t tmem_base;
 };
 constexpr size_t kTcSmem = 1024 + (size_t)kMaxChunks * kChunkBytes + 2 * kTileBytes + sizeof(TcTables);
 
+// Warps 0..15: transpose + epilogue.  Warp 16: MMA issue.  In steady state the warps meet only through mbarriers
+// (full / empty per accumulator buffer, afull per A tile), so a warp that finishes a chunk early runs ahead into the
+// next one and the tensor core works across tile boundaries; block-wide barriers happen only when the job changes.
 __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLaunch L) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem  = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem  = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* s_b   = smem;
     uint8_t* s_a   = smem + (size_t)kMaxChunks * kChunkBytes;
-    TcTables* tb   = (TcTables*)(s_a + 2 * kTileBytes);
+    TcTables* tb   = reinterpret_cast<TcTables*>(s_a + 2 * kTileBytes);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_mma  = warp == kEpiThreads / 32;
     const uint32_t row = tid & 127;       // coefficient of the tile: the same for the transpose and the epilogue
-    const uint32_t sub = tid >> 7;        // which quarter of the source limbs / of a chunk's outputs
-    const uint32_t N   = r.N;
+    const uint32_t sub = (tid >> 7) & 3;  // which quarter of the source limbs / of a chunk's outputs
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tb->tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        mbar_init(smem_u32(&tb->bar[0]), 1);
-        mbar_init(smem_u32(&tb->bar[1]), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&tb->full[b]), 1);
+            mbar_init(smem_u32(&tb->empty[b]), kEpiThreads / 32);
+            mbar_init(smem_u32(&tb->afull[b]), kEpiThreads / 32);
+        }
+        mbar_init(smem_u32(&tb->job), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tb->tmem_base;
-    const uint32_t bar0 = smem_u32(&tb->bar[0]), bar1 = smem_u32(&tb->bar[1]);
+    const uint32_t tmem   = tb->tmem_base;
+    const uint32_t full0  = smem_u32(&tb->full[0]), empty0 = smem_u32(&tb->empty[0]), afull0 = smem_u32(&tb->afull[0]);
     const uint32_t a_addr = smem_u32(s_a), b_addr = smem_u32(s_b);
 
     // contiguous share of the work list: at most a few job switches (= B reloads) per CTA
-    const uint32_t W = L.job[L.njobs - 1].work_end;
-    uint32_t w             = (uint32_t)(((uint64_t)W * blockIdx.x) / gridDim.x);
-    const uint32_t w_end   = (uint32_t)(((uint64_t)W * (blockIdx.x + 1)) / gridDim.x);
-    uint32_t ph0 = 0, ph1 = 0, cur = 0;
+    const uint32_t W     = L.job[L.njobs - 1].work_end;
+    uint32_t w           = (uint32_t)(((uint64_t)W * blockIdx.x) / gridDim.x);
+    const uint32_t w_end = (uint32_t)(((uint64_t)W * (blockIdx.x + 1)) / gridDim.x);
+    const uint32_t jobbar = smem_u32(&tb->job);
+    uint32_t g = 0, tcnt = 0, jcnt = 0;  // chunks / tiles / jobs this CTA has been through: accumulator buffer g & 1, A buffer tcnt & 1
     int jb_loaded = -1;
     uint64_t nxt[4];
 
-    // loads the four source residues of `row` for work item ww of job jb (Shoup-multiplied unless premultiplied)
+    // the four source residues of `row` for item `local` of job J: loads only, so that a prefetch never waits
     auto load_a = [&](const TcJob& J, uint32_t local, uint64_t (&y)[4]) {
         const uint32_t poly = local / L.tiles, tile = local - poly * L.tiles;
         const uint64_t* src = J.in + (size_t)poly * J.in_stride + (size_t)tile * kTileM + row;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const uint64_t* s4 = tb->src[4 * sub + u];
-            uint64_t v         = 0;
-            if (s4[3] != ~0ull) {
-                v = __ldg(src + (size_t)s4[3] * N);
-                if (!L.premultiplied)
-                    v = shoup(v, s4[1], s4[2], s4[0]);
-            }
-            y[u] = v;
+            const uint64_t off = tb->src[4 * sub + u][3];
+            y[u]               = off != ~0ull ? __ldg(src + off) : 0;
         }
     };
-    // [coefficient][limb bytes] image of the tile: row `row`, bytes [32 sub, 32 sub + 32), 128-byte swizzle
-    auto store_a = [&](uint32_t buf, const uint64_t (&y)[4]) {
+    // [coefficient][limb bytes] image of the tile: row `row`, bytes [32 sub, 32 sub + 32), 128-byte swizzle (Shoup-
+    // multiplied by QHatInvModq first unless the caller folded that into the inverse NTT); then this warp's share
+    // of the tile is announced to the MMA warp
+    auto store_a = [&](uint32_t buf, uint64_t (&y)[4]) {
+        if (!L.premultiplied) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t* s4 = tb->src[4 * sub + u];
+                y[u]               = shoup(y[u], s4[1], s4[2], s4[0]);  // padding rows: 0 * 0
+            }
+        }
         uint8_t* base = s_a + buf * kTileBytes + row * 128;
         *reinterpret_cast<uint4*>(base + (((2 * sub) ^ (row & 7)) << 4)) =
             make_uint4((uint32_t)y[0], (uint32_t)(y[0] >> 32), (uint32_t)y[1], (uint32_t)(y[1] >> 32));
         *reinterpret_cast<uint4*>(base + (((2 * sub + 1) ^ (row & 7)) << 4)) =
             make_uint4((uint32_t)y[2], (uint32_t)(y[2] >> 32), (uint32_t)y[3], (uint32_t)(y[3] >> 32));
-    };
-    auto issue = [&](uint32_t buf, uint32_t chunk, uint32_t bar) {  // thread 0 only
-        tc_fence_after();
-#pragma unroll
-        for (uint32_t k = 0; k < kK / 32; ++k)
-            mma_i8(tmem + buf * kChunkN, smem_desc(a_addr + cur * kTileBytes + k * 32),
-                   smem_desc(b_addr + chunk * kChunkBytes + k * 32), k);
-        mma_commit(bar);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(afull0 + 8 * buf);
     };
 
     while (w < w_end) {
@@ -230,99 +288,137 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
         const TcJob& J       = L.job[jb];
         const uint32_t wbase = jb ? L.job[jb - 1].work_end : 0;
         const uint32_t nout  = J.j1 - J.j0, nch = (nout + kChunkOut - 1) / kChunkOut;
+        const uint32_t local = w - wbase;
         if (jb != jb_loaded) {
-            // (re)load the job: tables, B image, first A tile -- everything of the previous job has been consumed
-            const BConvTcDesc* d = J.d;
-            if (tid < nch * kChunkOut) {
-                const uint32_t j   = min(J.j0 + tid, J.j1 - 1);
-                const ModConst& mc = r.mc[d->pidx[j]];
-                tb->dst[tid][0] = mc.q, tb->dst[tid][1] = mc.mu128_hi, tb->dst[tid][2] = mc.mu128_lo, tb->dst[tid][3] = d->ppos[j];
-            }
-            if (tid >= 256 && tid < 256 + 16) {
-                const uint32_t i = tid - 256;
-                const bool ok    = i < d->sizeQ;
-                tb->src[i][0]    = ok ? r.mc[d->qidx[i]].q : 1;
-                tb->src[i][1]    = ok ? d->qhatinv[2 * i] : 0;
-                tb->src[i][2]    = ok ? d->qhatinv[2 * i + 1] : 0;
-                tb->src[i][3]    = ok ? (uint64_t)d->qpos[i] : ~0ull;
-            }
-            const uint4* bsrc = reinterpret_cast<const uint4*>(d->bmat + (size_t)(J.j0 / kChunkOut) * kChunkBytes);
-            uint4* bdst       = reinterpret_cast<uint4*>(s_b);
-            for (uint32_t e = tid; e < nch * (kChunkBytes / 16); e += kTcThreads)
-                bdst[e] = __ldg(bsrc + e);
-            __syncthreads();  // tables visible to load_a
-            load_a(J, w - wbase, nxt);
-            store_a(cur, nxt);
-            fence_proxy_async();
+            // (re)load the job.  Every warp is past its last wait on the previous job's accumulators, so all of that
+            // job's MMAs have completed and nobody reads its tables any more once the barrier is passed.  Tables and
+            // B image arrive by bulk copies on one mbarrier; nobody stages them through registers.
             __syncthreads();
+            const BConvTcDesc* d = J.d;
+            if (tid == kEpiThreads) {
+                fence_proxy_async();  // earlier generic-proxy reads of the region vs the copy engine's writes
+                mbar_expect_tx(jobbar, nch * kChunkBytes + nout * 64 + 512);
+                for (uint32_t c = 0; c < nch; ++c)
+                    bulk_load(b_addr + c * kChunkBytes, d->bmat + (size_t)(J.j0 / kChunkOut + c) * kChunkBytes, kChunkBytes, jobbar);
+                bulk_load(smem_u32(&tb->dst[0][0]), d->dst_tab + (size_t)J.j0 * 8, nout * 64, jobbar);
+                bulk_load(smem_u32(&tb->src[0][0]), &d->src_tab[0][0], 512, jobbar);
+            }
+            mbar_wait(jobbar, jcnt & 1);
+            ++jcnt;
+            if (!is_mma) {
+                load_a(J, local, nxt);
+                store_a(tcnt & 1, nxt);
+            }
             jb_loaded = jb;
         }
-        const uint32_t local = w - wbase;
-        const uint32_t poly = local / L.tiles, tile = local - poly * L.tiles;
-        uint64_t* outp = J.out + (size_t)poly * J.out_stride + (size_t)tile * kTileM + row;
-
-        if (tid == 0) {
-            issue(0, 0, bar0);
-            if (nch > 1)
-                issue(1, 1, bar1);
-        }
         const bool have_next = (w + 1 < w_end) && (w + 1 < J.work_end);
-        if (have_next)
-            load_a(J, local + 1, nxt);  // in flight during the first epilogue
 
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            const uint32_t buf = ch & 1;
-            if (buf == 0) {
-                mbar_wait(bar0, ph0);
-                ph0 ^= 1;
-            }
-            else {
-                mbar_wait(bar1, ph1);
-                ph1 ^= 1;
-            }
-            tc_fence_after();
-            // this thread: outputs [kOutPerThr sub, kOutPerThr (sub + 1)) of the chunk, two at a time
+        if (is_mma) {
+            if (lane == 0) {
+                mbar_wait(afull0 + 8 * (tcnt & 1), (tcnt >> 1) & 1);
+                for (uint32_t ch = 0; ch < nch; ++ch, ++g) {
+                    const uint32_t b = g & 1;
+                    mbar_wait(empty0 + 8 * b, ((g >> 1) & 1) ^ 1);  // the first use of each buffer passes at once
+                    tc_fence_after();
 #pragma unroll
-            for (int pr = 0; pr < kOutPerThr / 2; ++pr) {
-                const uint32_t jl = ch * kChunkOut + kOutPerThr * sub + 2 * pr;  // output index within the job
-                if (jl < nout) {                                                 // warp-uniform
-                    uint32_t v[32];
-                    tmem_ld32(tmem + (((warp & 3) * 32) << 16) + buf * kChunkN + (kOutPerThr * sub + 2 * pr) * 16, v);
-#pragma unroll
-                    for (int o = 0; o < 2; ++o)
-                        if (jl + o < nout) {
-                            const uint64_t* dd = tb->dst[jl + o];
-                            uint64_t res       = fold_columns(v + 16 * o, dd[0], dd[1], dd[2]);
-                            if (L.debug_col) {
-                                res = 0;
-#pragma unroll
-                                for (int c = 0; c < 16; ++c)
-                                    res = (L.debug_col == (uint32_t)c + 1) ? v[16 * o + c] : res;
-                            }
-                            outp[(size_t)dd[3] * N] = res;
-                        }
+                    for (uint32_t k = 0; k < kK / 32; ++k)
+                        mma_i8(tmem + b * kChunkN, smem_desc(a_addr + (tcnt & 1) * kTileBytes + k * 32),
+                               smem_desc(b_addr + ch * kChunkBytes + k * 32), k);
+                    mma_commit(full0 + 8 * b);
                 }
             }
-            if (ch == 0 && have_next) {
-                store_a(cur ^ 1, nxt);
-                fence_proxy_async();
-            }
-            if (ch + 2 < nch) {
-                tc_fence_before();
-                __syncthreads();
-                if (tid == 0)
-                    issue(buf, ch + 2, buf ? bar1 : bar0);
+            __syncwarp();
+        }
+        else {
+            const uint32_t poly = local / L.tiles, tile = local - poly * L.tiles;
+            uint64_t* outp      = J.out + (size_t)poly * J.out_stride + (size_t)tile * kTileM + row;
+            if (have_next)
+                load_a(J, local + 1, nxt);  // in flight during the first epilogue
+            for (uint32_t ch = 0; ch < nch; ++ch, ++g) {
+                const uint32_t b = g & 1;
+                mbar_wait(full0 + 8 * b, (g >> 1) & 1);
+                tc_fence_after();
+                // this thread: outputs [4 sub, 4 sub + 4) of the chunk, as two pairs; the second pair's load is in
+                // flight while the first pair is folded and reduced, and the two reductions of a pair are independent
+                // instruction streams for the scheduler
+                const uint32_t jl0 = ch * kChunkOut + kOutPerThr * sub;  // index within the job; warp-uniform
+                const int nv       = jl0 >= nout ? 0 : (int)min((uint32_t)kOutPerThr, nout - jl0);
+                const uint32_t t0  = tmem + (((warp & 3) * 32) << 16) + b * kChunkN + kOutPerThr * sub * 16;
+                auto release = [&] {  // every load of this buffer has landed in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(empty0 + 8 * b);
+                };
+                auto reduce = [&](const uint32_t* v, const uint64_t* dd) {
+                    uint64_t res;
+                    if (OFHE_TC_FASTRED && dd[5] >= 32)  // warp-uniform
+                        res = fold_columns_fast(v, dd[0], dd[4], (uint32_t)dd[5], dd[6], dd[7]);
+                    else
+                        res = fold_columns(v, dd[0], dd[1], dd[2]);
+                    if (L.debug_col) {
+                        res = 0;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            res = (L.debug_col == (uint32_t)c + 1) ? v[c] : res;
+                    }
+                    return res;
+                };
+                auto emit2 = [&](const uint32_t (&v)[32], uint32_t jl, bool both) {
+                    const uint64_t* d0 = tb->dst[jl];
+                    const uint64_t* d1 = tb->dst[both ? jl + 1 : jl];
+                    const uint64_t r0 = reduce(v, d0), r1 = reduce(v + 16, d1);
+                    outp[d0[3]] = r0;
+                    if (both)
+                        outp[d1[3]] = r1;
+                };
+#if OFHE_TC_DB
+                uint32_t va[32], vb[32];
+                if (nv > 0) {
+                    tmem_ld32(t0, va);
+                    tmem_wait32(va);
+                    if (nv > 2)
+                        tmem_ld32(t0 + 32, vb);
+                    else
+                        release();
+                    emit2(va, jl0, nv > 1);
+                    if (nv > 2) {
+                        tmem_wait32(vb);
+                        release();
+                        emit2(vb, jl0 + 2, nv > 3);
+                    }
+                }
+                else
+                    release();
+#else
+                uint32_t va[32];
+                if (nv > 0) {
+                    tmem_ld32(t0, va);
+                    tmem_wait32(va);
+                    if (nv <= 2)
+                        release();
+                    emit2(va, jl0, nv > 1);
+                    if (nv > 2) {
+                        tmem_ld32(t0 + 32, va);
+                        tmem_wait32(va);
+                        release();
+                        emit2(va, jl0 + 2, nv > 3);
+                    }
+                }
+                else
+                    release();
+#endif
+                if (ch == 0 && have_next)
+                    store_a((tcnt + 1) & 1, nxt);
             }
         }
-        tc_fence_before();
-        __syncthreads();  // both accumulator buffers drained, the next A tile visible to the tensor core
-        if (have_next)
-            cur ^= 1;
-        else
-            jb_loaded = -1;  // next item (if any) belongs to another job: full reload
+        if (!have_next)
+            jb_loaded = -1;  // the next item (if any) belongs to another job: full reload
+        ++tcnt;
         ++w;
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -366,15 +462,32 @@ void bconv_finalize(const Ring& r, BConv& t) {
     bconv_tc_build_kernel<<<(total + 255) / 256, 256, 0, cudaStreamLegacy>>>(reinterpret_cast<const uint2*>(t.mat_d), t.sizeQ,
                                                                              t.sizeP, nch, t.tc_bmat_d);
     OFHE_CUDA(cudaGetLastError());
+    // per-limb tables, host computed: everything a job needs arrives in shared memory by three bulk copies
+    std::vector<uint64_t> hinv(2 * (size_t)t.sizeQ);
+    OFHE_CUDA(cudaMemcpy(hinv.data(), t.qhatinv_d, sizeof(uint64_t) * hinv.size(), cudaMemcpyDeviceToHost));
     BConvTcDesc h{};
-    h.sizeQ   = t.sizeQ;
-    h.sizeP   = t.sizeP;
-    h.bmat    = t.tc_bmat_d;
-    h.qhatinv = t.qhatinv_d;
-    for (uint32_t i = 0; i < t.sizeQ; ++i)
-        h.qidx[i] = t.qmap.idx[i], h.qpos[i] = t.qmap.pos[i];
-    for (uint32_t j = 0; j < t.sizeP; ++j)
-        h.pidx[j] = t.pmap.idx[j], h.ppos[j] = t.pmap.pos[j];
+    h.sizeQ = t.sizeQ;
+    h.sizeP = t.sizeP;
+    h.bmat  = t.tc_bmat_d;
+    for (uint32_t i = 0; i < 16; ++i) {
+        const bool ok   = i < t.sizeQ;
+        h.src_tab[i][0] = ok ? r.moduli[t.qmap.idx[i]] : 1;
+        h.src_tab[i][1] = ok ? hinv[2 * i] : 0;
+        h.src_tab[i][2] = ok ? hinv[2 * i + 1] : 0;
+        h.src_tab[i][3] = ok ? (uint64_t)t.qmap.pos[i] * r.N : ~0ull;
+    }
+    std::vector<uint64_t> dst(8 * (size_t)t.sizeP);
+    for (uint32_t j = 0; j < t.sizeP; ++j) {
+        const ModConst& mc = r.mc_h[t.pmap.idx[j]];
+        uint64_t* dd       = &dst[8 * (size_t)j];
+        dd[0] = mc.q, dd[1] = mc.mu128_hi, dd[2] = mc.mu128_lo, dd[3] = (uint64_t)t.pmap.pos[j] * r.N;
+        dd[4] = mc.mu, dd[5] = mc.k;
+        dd[6] = (uint64_t)((((unsigned __int128)1) << 64) % mc.q);
+        dd[7] = (uint64_t)((((unsigned __int128)1) << 96) % mc.q);
+    }
+    OFHE_CUDA(cudaMalloc(&t.tc_dst_tab_d, sizeof(uint64_t) * dst.size()));
+    h2d_blocking(t.tc_dst_tab_d, dst.data(), sizeof(uint64_t) * dst.size());
+    h.dst_tab = t.tc_dst_tab_d;
     OFHE_CUDA(cudaMalloc(&t.tc_desc_d, sizeof(BConvTcDesc)));
     h2d_blocking(t.tc_desc_d, &h, sizeof(h));  // also orders the build kernel (legacy stream) before any caller stream
 }

@@ -187,15 +187,17 @@ struct BConv {
     // tensor-core path (baseconv_tc.cu): byte-digit image of the matrix in the MMA's shared-memory layout and the
     // device-resident description of the conversion; built by bconv_finalize() for <= 16 source limbs
     uint8_t* tc_bmat_d = nullptr;
+    uint64_t* tc_dst_tab_d = nullptr;
     struct BConvTcDesc* tc_desc_d = nullptr;
     ~BConv();
 };
 struct BConvTcDesc {
+    // per source limb (padded to 16): q, QHatInvModq, its Shoup constant, word offset of the input row (~0: padding)
+    uint64_t src_tab[16][4];
     uint32_t sizeQ, sizeP;
     const uint8_t* bmat;      // [ceil(sizeP / 16)][256 rows][128 bytes], 128-byte swizzle
-    const uint64_t* qhatinv;  // [sizeQ][2]
-    uint16_t qidx[16], qpos[16];
-    uint16_t pidx[kMaxLimbs], ppos[kMaxLimbs];
+    // per target limb: p, mu128_hi, mu128_lo, word offset of the output row, mu, bit length, 2^64 mod p, 2^96 mod p
+    const uint64_t* dst_tab;  // [sizeP][8]
 };
 // called once by whoever fills a BConv (after mat_d / qhatinv_d / the maps are in place)
 void bconv_finalize(const Ring& r, BConv& t);
