@@ -40,7 +40,7 @@ METRIC = "ckks_evalmult_relin_per_s"
 UNIT = "mults/s"
 # kernels launched by one EvalMult (hks.cu): tensor 1, INTT 2, base conversion 3, NTT 2, inner product 1,
 # ModDown: INTT 2 + base conversion 1 + NTT 2 + (x-conv)*PInv+addend 2
-LAUNCHES_PER_STEP = 16
+LAUNCHES_PER_STEP = 14  # tensor, INTT x2, bconv (all digits), NTT x2, inner product, INTT x2, bconv, NTT x2, ModDown tail x2
 
 
 def measured_peak_gbs():

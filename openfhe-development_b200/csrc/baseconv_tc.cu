@@ -9,13 +9,16 @@
 //
 //   * residues and matrix entries are split into their 8 bytes -- no work, the bytes of the 64-bit words ARE the
 //     digits.  A tile of 128 coefficients becomes the K-major u8 operand A[128][K = 16 limbs x 8 bytes];
-//   * the matrix becomes B[(i,a)][(j,c)] = byte (c-a) of M[i][j]  (0 <= c-a < 8, else 0), c = 0..15: sixteen u8
+//   * the matrix becomes B[(i,a)][(j,c)] = byte (c-a) of M'[i][j]  (0 <= c-a < 8, else 0), c = 0..15: sixteen u8
 //     columns per target limb, one per digit weight 2^(8c) -- built once per conversion table, device resident in the
-//     exact shared-memory image (128-byte swizzle) the MMA reads;
+//     exact shared-memory image (128-byte swizzle) the MMA reads.  M'[i][j] = M[i][j] * 2^64 mod p_j: the matrix is
+//     kept in Montgomery form so that the reduction below needs no quotient estimate;
 //   * D[r][(j,c)] = sum_k A[r][k] B[k][(j,c)] <= 120 * 255^2 < 2^23 in s32, exact, accumulated in TMEM;
 //   * the epilogue reads the 15 column sums of an output with tcgen05.ld (one TMEM lane = one coefficient = one
-//     thread), rebuilds S = sum_c D_c 2^(8c) < 2^124 with 7 shift-adds, 4 funnel shifts and one 128-bit add, and
-//     reduces it with the same Barrett step as the CUDA-core kernel: the canonical residue, bit for bit.
+//     thread), rebuilds S' = sum_c D_c 2^(8c) = sum_i y_i M'[i][j] < 2^124 with 7 shift-adds, 4 funnel shifts and one
+//     128-bit add, and takes ONE 64-bit Montgomery step: t = (S' + (lo(S') * (-p^-1) mod 2^64) * p) / 2^64 = S (mod p)
+//     with t < 2p because S' < 16 * 2^60 * p, then one conditional subtraction: the canonical residue, bit for bit
+//     the value of the reference's 128-bit accumulate + BarrettUint128ModUint64.
 //
 // One persistent CTA per SM: 512 threads, all 512 TMEM columns as two 256-column accumulator buffers (16 target limbs
 // each), the whole B image of the job (<= 5 chunks of 32 KiB) and two 16 KiB A tiles in shared memory.  Thread 0
@@ -150,9 +153,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// S = sum_{c < 15} v[c] 2^(8c) (every v[c] < 2^23) reduced mod p: the value of BarrettUint128ModUint64 on the
-// exact dot product (utilities-int.h:60-100), i.e. what the reference's Mul128 / accumulate loop yields.
-__device__ __forceinline__ uint64_t fold_columns(const uint32_t* v, uint64_t p, uint64_t mu_hi, uint64_t mu_lo) {
+// S' = sum_{c < 15} v[c] 2^(8c) (every v[c] < 2^23, S' < 2^64 p) taken out of Montgomery form: S' 2^-64 mod p, canonical.
+// (S' + u p) is a multiple of 2^64 for u = lo(S') * ninv, ninv = -p^-1 mod 2^64; its quotient is hi(S') + hi(u p) +
+// [lo(S') != 0] < 2p.
+__device__ __forceinline__ uint64_t fold_columns(const uint32_t* v, uint64_t p, uint64_t ninv) {
     uint32_t e[8];
 #pragma unroll
     for (int k = 0; k < 7; ++k)
@@ -161,12 +165,11 @@ __device__ __forceinline__ uint64_t fold_columns(const uint32_t* v, uint64_t p, 
     const uint64_t a_lo = (uint64_t)e[0] | ((uint64_t)e[2] << 32), a_hi = (uint64_t)e[4] | ((uint64_t)e[6] << 32);
     const uint64_t b_lo = (uint64_t)e[1] | ((uint64_t)e[3] << 32), b_hi = (uint64_t)e[5] | ((uint64_t)e[7] << 32);
     const unsigned __int128 s = (((unsigned __int128)a_hi << 64) | a_lo) + ((((unsigned __int128)b_hi << 64) | b_lo) << 16);
-    return barrett128((uint64_t)(s >> 64), (uint64_t)s, p, mu_hi, mu_lo);
+    const uint64_t lo = (uint64_t)s, hi = (uint64_t)(s >> 64);
+    const uint64_t t  = hi + __umul64hi(lo * ninv, p) + (lo != 0);
+    return t >= p ? t - p : t;
 }
 
-#ifndef OFHE_TC_FASTRED
-#define OFHE_TC_FASTRED 1
-#endif
 #ifndef OFHE_TC_DB
 #define OFHE_TC_DB 0  // 1: the second output pair's TMEM load in flight during the first pair's reduction (64 live registers)
 #endif
@@ -196,7 +199,7 @@ __device__ __forceinline__ uint64_t fold_columns_fast(const uint32_t* v, uint64_
 // ---- the kernel --------------------------------------------------------------------------------------------------
 // dynamic shared memory (1024-byte aligned by hand): B image [kMaxChunks][32 KiB] | A tiles [2][16 KiB] | tables
 struct TcTables {
-    uint64_t dst[kMaxChunks * kChunkOut][8];  // p, mu128_hi, mu128_lo, word offset of the output row, mu, k, c2, c3
+    uint64_t dst[kMaxChunks * kChunkOut][4];  // p, -p^-1 mod 2^64, word offset of the output row, (pad)
     uint64_t src[16][4];                      // q, QHatInv, Shoup(QHatInv), word offset of the input row (~0: padding)
     uint64_t full[2];                         // accumulator buffer written   (1 arrival: tcgen05.commit)
     uint64_t empty[2];                        // accumulator buffer drained   (16 arrivals: one per epilogue warp)
@@ -297,10 +300,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
             const BConvTcDesc* d = J.d;
             if (tid == kEpiThreads) {
                 fence_proxy_async();  // earlier generic-proxy reads of the region vs the copy engine's writes
-                mbar_expect_tx(jobbar, nch * kChunkBytes + nout * 64 + 512);
+                mbar_expect_tx(jobbar, nch * kChunkBytes + nout * 32 + 512);
                 for (uint32_t c = 0; c < nch; ++c)
                     bulk_load(b_addr + c * kChunkBytes, d->bmat + (size_t)(J.j0 / kChunkOut + c) * kChunkBytes, kChunkBytes, jobbar);
-                bulk_load(smem_u32(&tb->dst[0][0]), d->dst_tab + (size_t)J.j0 * 8, nout * 64, jobbar);
+                bulk_load(smem_u32(&tb->dst[0][0]), d->dst_tab + (size_t)J.j0 * 4, nout * 32, jobbar);
                 bulk_load(smem_u32(&tb->src[0][0]), &d->src_tab[0][0], 512, jobbar);
             }
             mbar_wait(jobbar, jcnt & 1);
@@ -350,27 +353,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
                     if (lane == 0)
                         mbar_arrive(empty0 + 8 * b);
                 };
-                auto reduce = [&](const uint32_t* v, const uint64_t* dd) {
-                    uint64_t res;
-                    if (OFHE_TC_FASTRED && dd[5] >= 32)  // warp-uniform
-                        res = fold_columns_fast(v, dd[0], dd[4], (uint32_t)dd[5], dd[6], dd[7]);
-                    else
-                        res = fold_columns(v, dd[0], dd[1], dd[2]);
-                    if (L.debug_col) {
-                        res = 0;
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            res = (L.debug_col == (uint32_t)c + 1) ? v[c] : res;
-                    }
-                    return res;
-                };
+                // both reductions of a pair sit in ONE basic block (the path is chosen once per pair), so that the
+                // scheduler interleaves the two dependency chains
                 auto emit2 = [&](const uint32_t (&v)[32], uint32_t jl, bool both) {
                     const uint64_t* d0 = tb->dst[jl];
                     const uint64_t* d1 = tb->dst[both ? jl + 1 : jl];
-                    const uint64_t r0 = reduce(v, d0), r1 = reduce(v + 16, d1);
-                    outp[d0[3]] = r0;
+                    uint64_t r0 = fold_columns(v, d0[0], d0[1]);
+                    uint64_t r1 = fold_columns(v + 16, d1[0], d1[1]);
+                    if (L.debug_col) {
+                        r0 = r1 = 0;
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (L.debug_col == (uint32_t)c + 1)
+                                r0 = v[c], r1 = v[16 + c];
+                    }
+                    outp[d0[2]] = r0;
                     if (both)
-                        outp[d1[3]] = r1;
+                        outp[d1[2]] = r1;
                 };
 #if OFHE_TC_DB
                 uint32_t va[32], vb[32];
@@ -425,10 +424,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
 }
 
 // B image of a conversion table, built on the device from the 30-bit split matrix: chunk ch = targets [16 ch, 16 ch+16),
-// row n = 16 (j mod 16) + c, byte k = 8 i + a holds byte (c - a) of M[i][j]; rows of 128 bytes, 8-row atoms, 16-byte
-// units XOR-swizzled with the row (the SWIZZLE_128B layout the MMA descriptor names).
-__global__ void bconv_tc_build_kernel(const uint2* __restrict__ mat, uint32_t sizeQ, uint32_t sizeP, uint32_t nch,
-                                      uint8_t* __restrict__ bmat) {
+// row n = 16 (j mod 16) + c, byte k = 8 i + a holds byte (c - a) of M'[i][j] = M[i][j] * 2^64 mod p_j; rows of 128
+// bytes, 8-row atoms, 16-byte units XOR-swizzled with the row (the SWIZZLE_128B layout the MMA descriptor names).
+__global__ void bconv_tc_build_kernel(RingDev r, const uint2* __restrict__ mat, const uint16_t* __restrict__ pidx,
+                                      uint32_t sizeQ, uint32_t sizeP, uint32_t nch, uint8_t* __restrict__ bmat) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nch * kChunkBytes)
         return;
@@ -436,9 +435,11 @@ __global__ void bconv_tc_build_kernel(const uint2* __restrict__ mat, uint32_t si
     const uint32_t j = ch * kChunkOut + (n >> 4), c = n & 15, i = k >> 3, a = k & 7;
     uint8_t val = 0;
     if (j < sizeP && i < sizeQ && c >= a && c - a < 8) {
-        const uint2 m    = mat[(size_t)i * sizeP + j];
-        const uint64_t x = (uint64_t)m.x | ((uint64_t)m.y << 30);
-        val              = (uint8_t)(x >> (8 * (c - a)));
+        const ModConst mc  = r.mc[pidx[j]];
+        const uint2 m      = mat[(size_t)i * sizeP + j];
+        const uint64_t x   = (uint64_t)m.x | ((uint64_t)m.y << 30);
+        const uint64_t r64 = barrett128(1, 0, mc.q, mc.mu128_hi, mc.mu128_lo);  // 2^64 mod p
+        val                = (uint8_t)(mulmod(x, r64, mc) >> (8 * (c - a)));
     }
     bmat[(size_t)ch * kChunkBytes + (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 4) ^ (n & 7)) << 4) | (k & 15))] = val;
 }
@@ -459,9 +460,14 @@ void bconv_finalize(const Ring& r, BConv& t) {
     const uint32_t nch = (t.sizeP + kChunkOut - 1) / kChunkOut;
     OFHE_CUDA(cudaMalloc(&t.tc_bmat_d, (size_t)nch * kChunkBytes));
     const uint32_t total = nch * kChunkBytes;
-    bconv_tc_build_kernel<<<(total + 255) / 256, 256, 0, cudaStreamLegacy>>>(reinterpret_cast<const uint2*>(t.mat_d), t.sizeQ,
-                                                                             t.sizeP, nch, t.tc_bmat_d);
+    uint16_t* pidx_d     = nullptr;
+    OFHE_CUDA(cudaMalloc(&pidx_d, sizeof(uint16_t) * t.sizeP));
+    h2d_blocking(pidx_d, t.pmap.idx, sizeof(uint16_t) * t.sizeP);
+    bconv_tc_build_kernel<<<(total + 255) / 256, 256, 0, cudaStreamLegacy>>>(r.dev(), reinterpret_cast<const uint2*>(t.mat_d), pidx_d,
+                                                                             t.sizeQ, t.sizeP, nch, t.tc_bmat_d);
     OFHE_CUDA(cudaGetLastError());
+    OFHE_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    OFHE_CUDA(cudaFree(pidx_d));
     // per-limb tables, host computed: everything a job needs arrives in shared memory by three bulk copies
     std::vector<uint64_t> hinv(2 * (size_t)t.sizeQ);
     OFHE_CUDA(cudaMemcpy(hinv.data(), t.qhatinv_d, sizeof(uint64_t) * hinv.size(), cudaMemcpyDeviceToHost));
@@ -476,14 +482,15 @@ void bconv_finalize(const Ring& r, BConv& t) {
         h.src_tab[i][2] = ok ? hinv[2 * i + 1] : 0;
         h.src_tab[i][3] = ok ? (uint64_t)t.qmap.pos[i] * r.N : ~0ull;
     }
-    std::vector<uint64_t> dst(8 * (size_t)t.sizeP);
+    std::vector<uint64_t> dst(4 * (size_t)t.sizeP);
     for (uint32_t j = 0; j < t.sizeP; ++j) {
-        const ModConst& mc = r.mc_h[t.pmap.idx[j]];
-        uint64_t* dd       = &dst[8 * (size_t)j];
-        dd[0] = mc.q, dd[1] = mc.mu128_hi, dd[2] = mc.mu128_lo, dd[3] = (uint64_t)t.pmap.pos[j] * r.N;
-        dd[4] = mc.mu, dd[5] = mc.k;
-        dd[6] = (uint64_t)((((unsigned __int128)1) << 64) % mc.q);
-        dd[7] = (uint64_t)((((unsigned __int128)1) << 96) % mc.q);
+        const uint64_t p = r.moduli[t.pmap.idx[j]];
+        OFHE_REQUIRE(p & 1, "tensor-core base conversion: moduli must be odd");
+        uint64_t inv = p;  // Newton: p * inv = 1 mod 2^64 (p odd: 3 correct bits to start with, doubled 5 times)
+        for (int it = 0; it < 5; ++it)
+            inv *= 2 - p * inv;
+        uint64_t* dd = &dst[4 * (size_t)j];
+        dd[0] = p, dd[1] = 0 - inv, dd[2] = (uint64_t)t.pmap.pos[j] * r.N, dd[3] = 0;
     }
     OFHE_CUDA(cudaMalloc(&t.tc_dst_tab_d, sizeof(uint64_t) * dst.size()));
     h2d_blocking(t.tc_dst_tab_d, dst.data(), sizeof(uint64_t) * dst.size());

@@ -196,8 +196,8 @@ struct BConvTcDesc {
     uint64_t src_tab[16][4];
     uint32_t sizeQ, sizeP;
     const uint8_t* bmat;      // [ceil(sizeP / 16)][256 rows][128 bytes], 128-byte swizzle
-    // per target limb: p, mu128_hi, mu128_lo, word offset of the output row, mu, bit length, 2^64 mod p, 2^96 mod p
-    const uint64_t* dst_tab;  // [sizeP][8]
+    // per target limb: p, -p^-1 mod 2^64, word offset of the output row, (pad)
+    const uint64_t* dst_tab;  // [sizeP][4]
 };
 // called once by whoever fills a BConv (after mat_d / qhatinv_d / the maps are in place)
 void bconv_finalize(const Ring& r, BConv& t);

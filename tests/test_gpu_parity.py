@@ -228,6 +228,55 @@ def _hks_from_golden(gpu, g):
     return ring, hks
 
 
+def _crt_tables(moduli, src, dst):
+    """QHatInvModq and QHatModp of the basis {moduli[src]} towards {moduli[dst]} with exact integers
+    (dcrtpoly-impl.h:888-932 takes them from CryptoParametersRNS)."""
+    q = [int(moduli[i]) for i in src]
+    Q = 1
+    for v in q:
+        Q *= v
+    hatinv = np.array([pow((Q // qi) % qi, -1, qi) for qi in q], dtype=np.uint64)
+    mat = np.array([[(Q // qi) % int(moduli[j]) for j in dst] for qi in q], dtype=np.uint64)
+    return hatinv, mat
+
+
+@pytest.mark.parametrize("N,ns,nd", [(128, 15, 45), (128, 1, 3), (256, 16, 17), (256, 12, 90), (256, 3, 5),
+                                     (4096, 15, 45), (4096, 8, 33), (64, 15, 45)])
+def test_approx_switch_crt_basis_tensor_core_shapes(gpu, oracle, N, ns, nd):
+    """The tcgen05 base conversion (csrc/baseconv_tc.cu: <= 16 source limbs, N >= 128) over 1..6 accumulator chunks,
+    a ragged last chunk, exactly 16 source limbs, a conversion split into two jobs (> 80 targets) and, at N = 64, the
+    CUDA-core kernel the library falls back to -- all against the oracle's ApproxSwitchCRTBasis."""
+    ctx, m = gpu
+    p = m.ckks_paramgen(N, 89, 59, 60, 3, 0)
+    mod = p["moduli"]
+    ring = _ring(gpu, N, mod, p["roots"])
+    src = list(range(2, 2 + ns))
+    dst = [i for i in range(len(mod)) if i not in src][:nd]
+    x = seeded_residues(31 + ns, mod[src], N)
+    x[:, 0] = 0
+    x[:, 1] = mod[src] - np.uint64(1)
+    hatinv, mat = _crt_tables(mod, src, dst)
+    want = oracle.approx_switch_crt_basis(mod[src], hatinv, mod[dst], mat, x)
+    o = ctx.zeros(nd, N)
+    ring.approx_switch_crt_basis(src, dst, ctx.upload(x), o)
+    assert (ctx.download(o) == want).all()
+    ring.close()
+
+
+def test_approx_switch_crt_basis_cuda_core_kernel_still_exact():
+    """OFHE_BCONV_TC=0 keeps every conversion on the CUDA-core kernel (baseconv.cu); the switch is read once per
+    process, hence the child process.  Same shapes, exact big-integer expectation (tools/bconv_tc_check.py)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OFHE_BCONV_TC="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bconv_tc_check.py"), "parity"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PARITY PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("name", ["ckks_n64", "ckks_n128_flex"])
 def test_hybrid_keyswitch_golden(gpu, golden, name):
     """Every stage of a16-a19 and a14/a15 against vectors produced by the unmodified reference."""

@@ -32,7 +32,7 @@ def columns(moduli, src, dst, x):
     for jj, j in enumerate(dst):
         p = int(moduli[j])
         for i, qi in enumerate(q):
-            mm = (Q // qi) % p
+            mm = (((Q // qi) % p) << 64) % p  # the matrix is held in Montgomery form (csrc/baseconv_tc.cu)
             for a in range(8):
                 ya = ((ys[i] >> np.uint64(8 * a)) & np.uint64(255)).astype(np.int64)
                 for b in range(8):
