@@ -97,6 +97,8 @@ Hks::Level::~Level() {
         cudaFree(fold_modup_d);
     if (fold_moddown_d)
         cudaFree(fold_moddown_d);
+    if (pinv2_d)
+        cudaFree(pinv2_d);
 }
 
 Hks::Level& Hks::level(uint32_t sizeQl) {
@@ -199,7 +201,19 @@ Hks::Level& Hks::level(uint32_t sizeQl) {
             lv->map_Ql2.idx[n] = (uint16_t)i;
             lv->map_Ql2.pos[n] = (uint16_t)(b * sizeQl + i);
             fill_scalar(lv->pinv2, b * sizeQl + i, PInvModq[i], r.moduli[i]);
+            lv->tail_erow.pos[n] = (uint16_t)(b * sizeQlP + i);
+            lv->tail_drow.pos[n] = (uint16_t)(b * sizeQl + i);
         }
+    {
+        std::vector<uint64_t> pv(4 * (size_t)sizeQl);
+        for (uint32_t n = 0; n < 2 * sizeQl; ++n) {
+            const uint32_t i = lv->map_Ql2.idx[n];
+            pv[2 * n]     = lv->pinv2.s[i];
+            pv[2 * n + 1] = lv->pinv2.ss[i];
+        }
+        OFHE_CUDA(cudaMalloc(&lv->pinv2_d, sizeof(uint64_t) * pv.size()));
+        h2d_blocking(lv->pinv2_d, pv.data(), sizeof(uint64_t) * pv.size());
+    }
     // ---- CKKS rescale constants for dropping limb l = sizeQl-1 (ckksrns-cryptoparameters.cpp:60-83):
     //      A_i = floor(QlInv * Ql / q_l) mod q_i = -q_l^-1 mod q_i (q_i | Ql),  B_i = q_l^-1 mod q_i
     if (sizeQl >= 2) {
@@ -280,9 +294,13 @@ void Hks::mod_down2(uint32_t sizeQl, const uint64_t* e01, uint64_t* out01, const
     launch_ntt_inv(r, e01, p_tmp, lv.map_P2, st, &lv.gather_P2, lv.fold_moddown_d);  // times PHatInvModp
     // P -> Ql conversion of both polynomials in one launch                                     (:987-988)
     launch_bconv(r, *lv.moddown, p_tmp, conv_tmp, 2, (size_t)sizeP * N, (size_t)sizeQl * N, /*premultiplied=*/true, st);
-    // back to EVALUATION                                                                         (:1001)
+    // back to EVALUATION (:1001) and out = (e - conv) * P^-1 (+ addend) (:1002): the tail is the transform's epilogue
+    if (ntt_fwd_tail_fused(r)) {
+        NttTail tl{e01, addend01, out01, lv.pinv2_d, lv.tail_erow, lv.tail_drow};
+        launch_ntt_fwd(r, conv_tmp, conv_tmp, lv.map_Ql2, st, nullptr, &tl);
+        return;
+    }
     launch_ntt_fwd(r, conv_tmp, conv_tmp, lv.map_Ql2, st);
-    // out = (e - conv) * P^-1 (+ addend)                                                          (:1002)
     for (uint32_t b = 0; b < 2; ++b) {
         ScalarVec sv;
         for (uint32_t i = 0; i < sizeQl; ++i) {

@@ -38,6 +38,8 @@ struct Hks {
         uint64_t* fold_moddown_d = nullptr;  // [2*sizeP][4]: INTT constants with PHatInvModp folded in
         ~Level();
         ScalarVec pinv2;
+        uint64_t* pinv2_d = nullptr;  // [2*sizeQl][2] in map_Ql2's launch order: P^-1 mod q_i and its Shoup constant
+        PosMap tail_erow, tail_drow;  // rows of e01 [2][sizeQl+sizeP][N] / out01 [2][sizeQl][N] per launch limb of map_Ql2
         ScalarVec rescaleA, rescaleB;
     };
     std::map<uint32_t, std::unique_ptr<Level>> levels;

@@ -123,8 +123,20 @@ inline LimbMap make_map(const uint32_t* idx, uint32_t n) {
 // ---- kernel launchers (all asynchronous on `st`) ----------------------------------------------------
 // NTT: in -> out (in == out allowed).  Limb l of the launch lives at base + lm.pos[l] * N in both slabs.
 // If out_pos is given, limb l is read from in + lm.pos[l] * N and written to out + out_pos->pos[l] * N.
+// Optional epilogue of a forward transform's LAST pass: instead of storing NTT(x) for launch limb l the kernel stores
+//     dst[drow[l]] = (e[erow[l]] - NTT(x)) * scal[l]  (+ addend[drow[l]] if addend != nullptr; may alias dst)
+// -- the tail of ApproxModDown (dcrtpoly-impl.h:1002), so that the converted polynomial never returns to HBM.
+struct NttTail {
+    const uint64_t* e;
+    const uint64_t* addend;
+    uint64_t* dst;
+    const uint64_t* scal;  // device [lm.n][2]: the scalar and its Shoup constant
+    PosMap erow, drow;
+};
+// whether launch_ntt_fwd can fuse a tail for this ring (else the caller runs launch_sub_mul_scalars itself)
+bool ntt_fwd_tail_fused(const Ring& r);
 void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
-                    const PosMap* out_pos = nullptr);
+                    const PosMap* out_pos = nullptr, const NttTail* tail = nullptr);
 // `fold` (device, [lm.n][4]): per-limb replacement for (nInv, Shoup, Tinv[1]*nInv, Shoup) with an extra scalar
 // folded in, see make_inv_fold(); nullptr = plain inverse transform.
 void launch_ntt_inv(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,

@@ -322,6 +322,45 @@ __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_tile(RingDev r, ui
         d2[k] = make_ulonglong2(x[2 * k], x[2 * k + 1]);
 #endif
 }
+// the same tile pass with the ApproxModDown tail as its epilogue (NttTail, internal.h): thread t ends with the 16
+// canonical values of tile offsets 16t .. 16t+15 in registers and combines them with the minuend / addend rows on
+// their way out -- the transform's result itself is never stored
+template <int A>
+__global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_fwd_tile_tail(RingDev r, const uint64_t* data, LimbMap lm, NttTail tl) {
+    __shared__ __align__(16) uint64_t sm[kTile];
+    const uint32_t limb = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+    const uint32_t mi   = lm.idx[limb];
+    const Mod m         = make_mod(r.mc[mi]);
+    const uint64_t* p   = data + (size_t)lm.pos[limb] * r.N + (size_t)tile * kTile;
+    const Twiddle* tw   = r.tw_fwd + (size_t)mi * r.N;
+    uint64_t x[16];
+    prefetch_round(tw, (1u << A) + tile);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        x[k] = p[t + 256 * k];
+    TwWin ha;
+    tw_preload<false>(ha, tw, (1u << A) + tile);
+    fwd_tile_rounds<12 + A>(sm, x, ha, tw, tile, m, t);
+    const uint64_t q = r.mc[mi].q, s = tl.scal[2 * limb], ss = tl.scal[2 * limb + 1];
+    const size_t off = (size_t)tile * kTile + 16 * t;
+    const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(tl.e + (size_t)tl.erow.pos[limb] * r.N + off);
+    const ulonglong2* a2 =
+        tl.addend ? reinterpret_cast<const ulonglong2*>(tl.addend + (size_t)tl.drow.pos[limb] * r.N + off) : nullptr;
+    ulonglong2* d2 = reinterpret_cast<ulonglong2*>(tl.dst + (size_t)tl.drow.pos[limb] * r.N + off);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const ulonglong2 ev = e2[k];
+        ulonglong2 o;
+        o.x = shoup(submod(ev.x, x[2 * k], q), s, ss, q);
+        o.y = shoup(submod(ev.y, x[2 * k + 1], q), s, ss, q);
+        if (a2) {
+            const ulonglong2 z = a2[k];
+            o.x = addmod(o.x, z.x, q);
+            o.y = addmod(o.y, z.y, q);
+        }
+        d2[k] = o;
+    }
+}
 template <int A>
 __global__ void __launch_bounds__(256, OFHE_NTT_MINB) ntt_inv_tile(RingDev r, const uint64_t* in, uint64_t* out,
                                                                      LimbMap lm, PosMap op) {
@@ -640,7 +679,8 @@ bool ntt_stream() {
     return on;
 }
 template <int A>
-void fwd_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st) {
+void fwd_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, const PosMap& op, cudaStream_t st,
+               const NttTail* tail = nullptr) {
     static const bool once = [] {
         OFHE_CUDA(cudaFuncSetAttribute(ntt_fwd_tile_stream<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)kTileBytes));
         return true;
@@ -652,7 +692,11 @@ void fwd_split(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& 
         PosMap o2;
         sub_maps(lm, op, s, std::min(chunk, lm.n - s), l2, o2);
         ntt_fwd_strided<A><<<dim3((r.N >> A) / 256, l2.n), 256, 0, st>>>(r.dev(), in, out, l2, o2);
-        if (ntt_stream()) {
+        if (tail) {
+            OFHE_REQUIRE(s == 0 && l2.n == lm.n, "fused transform tail: chunked launches are not supported");
+            ntt_fwd_tile_tail<A><<<dim3(r.N / kTile, l2.n), 256, 0, st>>>(r.dev(), out, on_output(l2, o2), *tail);
+        }
+        else if (ntt_stream()) {
             const uint32_t items = l2.n << A;
             ntt_fwd_tile_stream<A><<<stream_grid(r, items), 256, 2 * kTileBytes, st>>>(r.dev(), out, on_output(l2, o2), items);
         }
@@ -723,10 +767,26 @@ void ntt_cluster_occupancy(uint32_t logN, int out[2]) {
     }
 }
 
+bool ntt_fwd_tail_fused(const Ring& r) {
+    if (r.logN < 13 || r.logN > 17)
+        return false;
+    // OFHE_NTT_TAIL=1 fuses the ModDown tail into the tile pass.  Bit-identical, but measured on B200 (N = 2^16, 2 x 45
+    // limbs, profiles/r02u_*): the tile pass grows from 60 to 89 us -- each thread owns 16 CONTIGUOUS outputs, so the
+    // minuend / addend loads are 16-byte pieces 128 bytes apart across a warp -- against 30 us for the two stand-alone
+    // tail launches: 492 vs 497 us for one EvalMult alone, and 2038 vs 2127 mults/s with four in flight, where the
+    // HBM-bound tail kernels of one multiplication hide under the integer-bound kernels of another.  Default off.
+    static const bool on = [] {
+        const char* e = getenv("OFHE_NTT_TAIL");
+        return e && e[0] == '1';
+    }();
+    return on && (r.logN == 17 || ntt_mode(true, (int)r.logN - 12) == 1) && ntt_chunk_limbs(r) >= (uint32_t)kMaxLimbs;
+}
+
 void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const LimbMap& lm, cudaStream_t st,
-                    const PosMap* out_pos) {
+                    const PosMap* out_pos, const NttTail* tail) {
     if (lm.n == 0)
         return;
+    OFHE_REQUIRE(!tail || ntt_fwd_tail_fused(r), "fused transform tail is not available for this ring");
     const PosMap op = default_pos(lm, out_pos);
     if (r.logN < 12) {
         uint32_t th = r.N / 2 < 32 ? 32 : (r.N / 2 > 512 ? 512 : r.N / 2);
@@ -735,11 +795,11 @@ void launch_ntt_fwd(const Ring& r, const uint64_t* in, uint64_t* out, const Limb
     else {
         switch (r.logN - 12) {
             case 0: fwd_cluster<0>(r, in, out, lm, op, st); break;
-            case 1: ntt_mode(true, 1) ? fwd_split<1>(r, in, out, lm, op, st) : fwd_cluster<1>(r, in, out, lm, op, st); break;
-            case 2: ntt_mode(true, 2) ? fwd_split<2>(r, in, out, lm, op, st) : fwd_cluster<2>(r, in, out, lm, op, st); break;
-            case 3: ntt_mode(true, 3) ? fwd_split<3>(r, in, out, lm, op, st) : fwd_cluster<3>(r, in, out, lm, op, st); break;
-            case 4: ntt_mode(true, 4) ? fwd_split<4>(r, in, out, lm, op, st) : fwd_cluster<4>(r, in, out, lm, op, st); break;
-            case 5: fwd_split<5>(r, in, out, lm, op, st); break;
+            case 1: ntt_mode(true, 1) ? fwd_split<1>(r, in, out, lm, op, st, tail) : fwd_cluster<1>(r, in, out, lm, op, st); break;
+            case 2: ntt_mode(true, 2) ? fwd_split<2>(r, in, out, lm, op, st, tail) : fwd_cluster<2>(r, in, out, lm, op, st); break;
+            case 3: ntt_mode(true, 3) ? fwd_split<3>(r, in, out, lm, op, st, tail) : fwd_cluster<3>(r, in, out, lm, op, st); break;
+            case 4: ntt_mode(true, 4) ? fwd_split<4>(r, in, out, lm, op, st, tail) : fwd_cluster<4>(r, in, out, lm, op, st); break;
+            case 5: fwd_split<5>(r, in, out, lm, op, st, tail); break;
             default: throw Error("ring dimension above 2^17 is not supported");
         }
     }

@@ -277,6 +277,21 @@ def test_approx_switch_crt_basis_cuda_core_kernel_still_exact():
     assert r.returncode == 0 and "PARITY PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_fused_moddown_tail_variant_still_exact():
+    """OFHE_NTT_TAIL=1 (measurement switch, default off) makes the ApproxModDown tail the epilogue of the forward NTT's
+    tile pass (ntt_fwd_tile_tail, csrc/ntt.cu).  The switch is read once per process, hence the child: the full-size
+    config-2 EvalMult against the oracle with the fused kernel."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OFHE_NTT_TAIL="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_config2_full_size"], env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("name", ["ckks_n64", "ckks_n128_flex"])
 def test_hybrid_keyswitch_golden(gpu, golden, name):
     """Every stage of a16-a19 and a14/a15 against vectors produced by the unmodified reference."""
