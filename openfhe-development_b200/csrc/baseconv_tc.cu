@@ -28,6 +28,7 @@
 // the two polynomials of a ModDown) are one launch: a job list, work = (job, polynomial, tile).
 //
 // Eligibility: mode 0 (approximate conversion), <= 16 source limbs, N >= 128.  Everything else stays on baseconv.cu.
+#include <atomic>
 #include <cstdlib>
 #include <vector>
 
@@ -504,11 +505,14 @@ bool bconv_tc_eligible(const Ring& r, const BConv& t) {
 }
 
 void launch_bconv_tc(const Ring& r, const BConvJob* jobs, uint32_t njobs, bool premultiplied, cudaStream_t st) {
-    static const bool attr_set = [] {
+    // the opt-in for > 48 KiB of dynamic shared memory is per device: once for every device this process launches on
+    static std::atomic<bool> attr_set[64];
+    const int dev = r.ctx->device;
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
         OFHE_CUDA(cudaFuncSetAttribute(bconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        return true;
-    }();
-    (void)attr_set;
+        if (dev >= 0 && dev < 64)
+            attr_set[dev].store(true, std::memory_order_release);
+    }
     TcLaunch L{};
     L.tiles         = r.N / kTileM;
     L.premultiplied = premultiplied ? 1u : 0u;

@@ -213,10 +213,21 @@ void Shard::evalmult_b(uint32_t sizeQl, const uint64_t* gatherQ, const uint64_t*
     uint64_t* e01    = digits + (size_t)dnum * nown * N;
     if (nown == 0)
         return;
+    // :360-365 -- every digit's conversion in ONE tensor-core launch when they all qualify
+    bool all_tc = lv.n_digits <= 4;
+    BConvJob jobs[4];
+    uint32_t njobs = 0;
+    for (uint32_t j = 0; j < lv.n_digits && all_tc; ++j)
+        if (lv.modup[j]) {
+            all_tc        = bconv_tc_eligible(r, *lv.modup[j]);
+            jobs[njobs++] = BConvJob{lv.modup[j].get(), gatherQ, digits + (size_t)j * nown * N, 1, 0, 0};
+        }
+    if (all_tc && njobs)
+        launch_bconv_tc(r, jobs, njobs, /*premultiplied=*/true, st);
     for (uint32_t j = 0; j < lv.n_digits; ++j) {
         uint64_t* D = digits + (size_t)j * nown * N;
-        if (lv.modup[j])
-            launch_bconv(r, *lv.modup[j], gatherQ, D, 1, 0, 0, /*premultiplied=*/true, st);  // :360-365
+        if (lv.modup[j] && !all_tc)
+            launch_bconv(r, *lv.modup[j], gatherQ, D, 1, 0, 0, /*premultiplied=*/true, st);
         if (lv.own_count[j])                                                                   // :372-373
             OFHE_CUDA(cudaMemcpyAsync(D + (size_t)lv.own_first[j] * N, c2 + (size_t)lv.own_first[j] * N,
                                       sizeof(uint64_t) * lv.own_count[j] * N, cudaMemcpyDeviceToDevice, st));

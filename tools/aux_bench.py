@@ -256,10 +256,30 @@ def config5_sharded(m, torch, ctx, dist, rank, world):
                         "16*N*L algorithmic bytes per transform", "n_gpus": world, "peak_gbs_per_gpu": peak, "rows": rows}
 
 
+def base_conversion(m, torch, ctx):
+    """RNS fast base conversion 15 -> 45 limbs at N = 2^16 (one ModUp digit of config 2), the tensor-core kernel
+    (csrc/baseconv_tc.cu) unless OFHE_BCONV_TC=0: algorithmic bytes 8*N*(15+45)."""
+    N = 1 << 16
+    p = m.ckks_paramgen(N, 44, 59, 60, 3, 0)
+    ring = m.Ring(ctx, N, p["moduli"], p["roots"])
+    src, dst = list(range(15)), list(range(15, 60))
+    d, o = ctx.zeros(15, N), ctx.zeros(45, N)
+    ring.fill_uniform(d, src, 3)
+    us = _timeit(torch, lambda: ring.approx_switch_crt_basis(src, dst, d, o), 30, warm=5)
+    ring.close()
+    alg = 8.0 * N * 60
+    return {"workload": "ApproxSwitchCRTBasis 15 -> 45 limbs, N=2^16 (QHatInv multiply included)", "us": us,
+            "kernel": "bconv_tc_kernel (tcgen05.mma kind::i8, TMEM accumulators)" if os.environ.get("OFHE_BCONV_TC", "1") != "0"
+            else "bconv_kernel (CUDA cores)",
+            "algorithmic_gbs": alg / us / 1e3, "frac_of_measured_hbm": alg / us / 1e3 / _peak(),
+            "cuda_core_kernel_us_committed": 50.2, "source": "profiles/r02s_kernels_tc_vs_cuda.json"}
+
+
 def run(m, torch, ctx):
     out = {}
     for name, fn in (("config1_ntt4096_single_limb", config1), ("config2_resident_chain_and_rotations", config2_resident),
-                     ("config3_bfv_evalmult_n15", config3), ("config5_ntt_sweep", config5)):
+                     ("config3_bfv_evalmult_n15", config3), ("base_conversion_15_45", base_conversion),
+                     ("config5_ntt_sweep", config5)):
         try:
             out[name] = fn(m, torch, ctx)
         except Exception as ex:
