@@ -294,6 +294,26 @@ int ofhe_shard_evalmult_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* c
                                uint64_t* out_d, uint64_t* const* gatherQ_of_rank_h, void* stream);
 int ofhe_shard_evalmult_b_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* evk_a_d, const uint64_t* evk_b_d,
                                uint64_t* const* gatherQ_of_rank_h, uint64_t* const* gatherP_of_rank_h, void* stream);
+/* ---- limb-sharded EvalAutomorphism / EvalRotate and rescale: the other two operations a bootstrapping-sized circuit
+ *      (BASELINE config 4) needs besides EvalMult, on the same ownership plan and gather buffers.
+ *      Rotation (LeveledSHEBase::EvalAutomorphism, base-leveledshe.cpp:382-422 = KeySwitchInPlace + automorphism):
+ *        rotate_a, exchange gatherQ, ofhe_shard_evalmult_b with the ROTATION key's local rows, exchange gatherP,
+ *        rotate_c.  ct_d / tmp_d / out_d: [2][nOwnQ][N]; k: the automorphism index (ofhe_find_automorphism_index).
+ *      Rescale (DCRTPolyImpl::DropLastElementAndScale, dcrtpoly-impl.h:693-712, both polynomials): rescale_a on
+ *        every rank (only the owner of limb sizeQl-1 works: it writes the limb's coefficient form into gatherL [2][N]),
+ *        broadcast of gatherL from that owner (or the _push form + one peer barrier), rescale_b.
+ *        out_d: [2][nOwnQ(sizeQl-1)][N].                                                                              */
+int ofhe_shard_rotate_a(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* tmp_d, uint64_t* gatherQ_d,
+                        void* stream);
+int ofhe_shard_rotate_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* tmp_d,
+                             uint64_t* const* gatherQ_of_rank_h, void* stream);
+int ofhe_shard_rotate_c(ofhe_shard* s, uint32_t sizeQl, uint32_t k, const uint64_t* gatherP_d, uint64_t* tmp_d,
+                        uint64_t* out_d, void* stream);
+int ofhe_shard_rescale_a(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* gatherL_d, void* stream);
+int ofhe_shard_rescale_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* const* gatherL_of_rank_h,
+                              void* stream);
+int ofhe_shard_rescale_b(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, const uint64_t* gatherL_d, uint64_t* out_d,
+                         void* stream);
 /* flags buffers: ofhe_peer_flags_words(world, n_barriers) zero-initialised words per rank.  The kernel bumps this
  * rank's epoch for barrier `index`, publishes it to every rank (release, system scope) and waits until every rank's
  * arrival for that epoch is visible (acquire).  A wait longer than 10 s of wall clock (%globaltimer) counts a timeout

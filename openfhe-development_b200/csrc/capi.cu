@@ -985,6 +985,50 @@ int ofhe_shard_evalmult_b_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* e
         s->s->evalmult_b(sizeQl, gatherQ_of_rank_h[s->s->rank], evk_a_d, evk_b_d, po.base[s->s->rank], S(stream), &po);
     });
 }
+int ofhe_shard_rotate_a(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* tmp_d, uint64_t* gatherQ_d,
+                        void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        s->s->rotate_a(sizeQl, ct_d, tmp_d, gatherQ_d, S(stream));
+    });
+}
+int ofhe_shard_rotate_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* tmp_d,
+                             uint64_t* const* gatherQ_of_rank_h, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        const PeerOut po = peer_list(*s->s, gatherQ_of_rank_h);
+        s->s->rotate_a(sizeQl, ct_d, tmp_d, po.base[s->s->rank], S(stream), &po);
+    });
+}
+int ofhe_shard_rotate_c(ofhe_shard* s, uint32_t sizeQl, uint32_t k, const uint64_t* gatherP_d, uint64_t* tmp_d,
+                        uint64_t* out_d, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        OFHE_REQUIRE((k & 1u) && k < 2 * s->s->ring->N, "automorphism index must be odd and below 2N");
+        s->s->rotate_c(sizeQl, k, gatherP_d, tmp_d, out_d, S(stream));
+    });
+}
+int ofhe_shard_rescale_a(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* gatherL_d, void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        s->s->rescale_a(sizeQl, ct_d, gatherL_d, S(stream));
+    });
+}
+int ofhe_shard_rescale_a_push(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, uint64_t* const* gatherL_of_rank_h,
+                              void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        const PeerOut po = peer_list(*s->s, gatherL_of_rank_h);
+        s->s->rescale_a(sizeQl, ct_d, po.base[s->s->rank], S(stream), &po);
+    });
+}
+int ofhe_shard_rescale_b(ofhe_shard* s, uint32_t sizeQl, const uint64_t* ct_d, const uint64_t* gatherL_d, uint64_t* out_d,
+                         void* stream) {
+    return guard([&] {
+        use(s->s->ring);
+        s->s->rescale_b(sizeQl, ct_d, gatherL_d, out_d, S(stream));
+    });
+}
 size_t ofhe_peer_flags_words(uint32_t world, uint32_t n_barriers) {
     return (size_t)n_barriers * (world + 2);
 }

@@ -155,8 +155,16 @@ const uint32_t* ring_automap(Ring* r, uint32_t k, cudaStream_t st) {
         return it->second;
     uint32_t* d = nullptr;
     OFHE_CUDA(cudaMalloc(&d, sizeof(uint32_t) * r->N));
-    launch_build_automap(r->N, r->logN, k, d, st);
-    OFHE_CUDA(cudaStreamSynchronize(st));  // one-time: later calls may come from other streams
+    // one-time build on a PRIVATE stream, finished before the pointer is handed out: later calls may come from any
+    // stream, and the caller's stream must not be waited for here -- it may hold a device barrier whose partner
+    // ranks this very host thread has yet to launch (virtual ranks of one process, tests/test_gpu_shard.py)
+    (void)st;
+    cudaStream_t tmp;
+    OFHE_CUDA(cudaStreamCreateWithFlags(&tmp, cudaStreamNonBlocking));
+    launch_build_automap(r->N, r->logN, k, d, tmp);
+    const cudaError_t e = cudaStreamSynchronize(tmp);
+    cudaStreamDestroy(tmp);
+    OFHE_CUDA(e);
     r->automaps[k] = d;
     return d;
 }

@@ -178,6 +178,25 @@ Shard::Level& Shard::level(uint32_t sizeQl) {
                 }
             }
     }
+    // rescale: owned limbs below the last one keep their local rows; constants as in Hks::level
+    lv->map_low.n = 0;
+    if (sizeQl >= 2) {
+        const uint32_t l = sizeQl - 1;
+        for (uint32_t t = 0; t < nq; ++t) {
+            const uint32_t i = lv->ownQ[t];
+            if (i == l) {
+                lv->last_row = (int)t;
+                continue;
+            }
+            const uint64_t qi = r.moduli[i], B = hm::inv(r.moduli[l] % qi, qi);
+            const uint32_t n  = lv->map_low.n;
+            lv->rescaleA.s[n]  = qi - B;
+            lv->rescaleA.ss[n] = hm::shoup_const(qi - B, qi);
+            lv->rescaleB.s[n]  = B;
+            lv->rescaleB.ss[n] = hm::shoup_const(B, qi);
+            put(lv->map_low, i, t);
+        }
+    }
     auto& ref      = *lv;
     levels[sizeQl] = std::move(lv);
     return ref;
@@ -255,6 +274,60 @@ void Shard::evalmult_c(uint32_t sizeQl, const uint64_t* gatherP, uint64_t* out, 
     for (uint32_t b = 0; b < 2; ++b)  // (e - conv) * P^-1 + (c0 | c1)            :1002, base-leveledshe.cpp:209-210
         launch_sub_mul_scalars(r, out + b * nq * N, e01 + b * nown * N, conv + b * nq * N, lv.pinv, out + b * nq * N,
                                lv.map_q, st);
+}
+
+void Shard::rotate_a(uint32_t sizeQl, const uint64_t* ct, uint64_t* tmp, uint64_t* gatherQ, cudaStream_t st,
+                     const PeerOut* peers) {
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, P = (size_t)lv.nOwnQ * N;
+    uint64_t* c2   = scratch(sizeQl);  // the polynomial to switch sits where evalmult_a leaves c2 (evalmult_b reads it)
+    if (lv.nOwnQ == 0)
+        return;
+    // KeySwitchInPlace on (c0, c1): (c0 + ab0, ab1) with ab = KeySwitchCore(c1)           (keyswitch-hybrid.cpp:199-214)
+    OFHE_CUDA(cudaMemcpyAsync(c2, ct + P, sizeof(uint64_t) * P, cudaMemcpyDeviceToDevice, st));
+    OFHE_CUDA(cudaMemcpyAsync(tmp, ct, sizeof(uint64_t) * P, cudaMemcpyDeviceToDevice, st));
+    OFHE_CUDA(cudaMemsetAsync(tmp + P, 0, sizeof(uint64_t) * P, st));
+    launch_ntt_inv(r, c2, gatherQ, lv.map_q, st, &lv.gatherq_pos, lv.fold_q_d, peers);
+}
+
+void Shard::rotate_c(uint32_t sizeQl, uint32_t k, const uint64_t* gatherP, uint64_t* tmp, uint64_t* out, cudaStream_t st) {
+    Level& lv = level(sizeQl);
+    if (lv.nOwnQ == 0)
+        return;
+    evalmult_c(sizeQl, gatherP, tmp, st);
+    // both polynomials through the automorphism gather, limb by limb                         (base-leveledshe.cpp:414-420)
+    launch_automorphism(*ring, out, tmp, ring_automap(ring, k, st), 2 * lv.nOwnQ, st);
+}
+
+void Shard::rescale_a(uint32_t sizeQl, const uint64_t* ct, uint64_t* gatherL, cudaStream_t st, const PeerOut* peers) {
+    OFHE_REQUIRE(sizeQl >= 2, "rescale needs at least two limbs");
+    Level& lv = level(sizeQl);
+    if (lv.last_row < 0)
+        return;  // another rank owns the dropped limb
+    LimbMap two;
+    PosMap dst;
+    two.n = 0;
+    for (uint32_t b = 0; b < 2; ++b) {
+        dst.pos[two.n] = (uint16_t)b;
+        put(two, sizeQl - 1, b * lv.nOwnQ + (uint32_t)lv.last_row);
+    }
+    launch_ntt_inv(*ring, ct, gatherL, two, st, &dst, nullptr, peers);  // dcrtpoly-impl.h:696-697, both polynomials
+}
+
+void Shard::rescale_b(uint32_t sizeQl, const uint64_t* ct, const uint64_t* gatherL, uint64_t* out, cudaStream_t st) {
+    OFHE_REQUIRE(sizeQl >= 2, "rescale needs at least two limbs");
+    Level& lv      = level(sizeQl);
+    const Ring& r  = *ring;
+    const size_t N = r.N, nq = lv.nOwnQ, nlow = lv.map_low.n;
+    if (nlow == 0)
+        return;
+    uint64_t* t = scratch(sizeQl);
+    for (uint32_t b = 0; b < 2; ++b) {
+        launch_switch_modulus_scale(r, t, gatherL + b * N, sizeQl - 1, lv.rescaleA, lv.map_low, st);  // :703-704
+        launch_ntt_fwd(r, t, t, lv.map_low, st);                                                      // :705-706
+        launch_mul_scalars_add(r, out + b * nlow * N, ct + b * nq * N, lv.rescaleB, t, lv.map_low, st);  // :707-708
+    }
 }
 
 }  // namespace ofhe

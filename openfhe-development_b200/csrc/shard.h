@@ -29,6 +29,11 @@ struct Shard {
         uint64_t* fold_q_d = nullptr;
         uint64_t* fold_p_d = nullptr;
         ScalarVec pinv;
+        // rescale (drop the last limb l = sizeQl-1): the owned limbs below l in local order, their constants
+        // -q_l^-1 and q_l^-1 mod q_i (ckksrns-cryptoparameters.cpp:60-83), and where the last limb lives
+        LimbMap map_low;
+        ScalarVec rescaleA, rescaleB;
+        int last_row = -1;  // local row of limb l if this rank owns it
         ~Level();
     };
     std::map<uint32_t, std::unique_ptr<Level>> levels;
@@ -52,6 +57,21 @@ struct Shard {
                     uint64_t* gatherP, cudaStream_t st, const PeerOut* peers = nullptr);
     // phase C (after the all-gather of gatherP): ModDown of the owned Q rows and the final additions into out
     void evalmult_c(uint32_t sizeQl, const uint64_t* gatherP, uint64_t* out, cudaStream_t st);
+
+    // ---- limb-sharded EvalAutomorphism / EvalRotate (base-leveledshe.cpp:382-422: KeySwitchInPlace, then the
+    //      automorphism of both polynomials).  ct, tmp, out: [2][nOwnQ][N] local rows.  Sequence: rotate_a, exchange of
+    //      gatherQ, evalmult_b with the rotation key's rows, exchange of gatherP, rotate_c.
+    // phase A: c1 becomes the polynomial to switch (its INTT * QHatInv goes to gatherQ), tmp = (c0 | 0)
+    void rotate_a(uint32_t sizeQl, const uint64_t* ct, uint64_t* tmp, uint64_t* gatherQ, cudaStream_t st,
+                  const PeerOut* peers = nullptr);
+    // phase C: tmp += ModDown(e0 | e1) on the owned rows, out = automorphism_k(tmp) (limb-local)
+    void rotate_c(uint32_t sizeQl, uint32_t k, const uint64_t* gatherP, uint64_t* tmp, uint64_t* out, cudaStream_t st);
+
+    // ---- limb-sharded rescale (DCRTPolyImpl::DropLastElementAndScale, dcrtpoly-impl.h:693-712) of a 2-element
+    //      ciphertext: the owner of the last limb sends its coefficient form to everyone (gatherL [2][N], one exchange),
+    //      every rank then finishes its own limbs.  out: [2][nOwnQ(sizeQl-1)][N].
+    void rescale_a(uint32_t sizeQl, const uint64_t* ct, uint64_t* gatherL, cudaStream_t st, const PeerOut* peers = nullptr);
+    void rescale_b(uint32_t sizeQl, const uint64_t* ct, const uint64_t* gatherL, uint64_t* out, cudaStream_t st);
 };
 
 }  // namespace ofhe

@@ -105,6 +105,12 @@ SIGNATURES = {
     "ofhe_bfv_evalmult": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_a_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "ofhe_shard_evalmult_b_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_rotate_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_rotate_a_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_rotate_c": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "ofhe_shard_rescale_a": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_shard_rescale_a_push": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "ofhe_shard_rescale_b": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "ofhe_peer_flags_words": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "ofhe_peer_barrier": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "ofhe_peer_barrier_timeouts": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _u64p]),
@@ -679,6 +685,36 @@ class Shard:
         self.phase_b_push(sizeQl, evk_a, evk_b, gq_of_rank, gp_of_rank)
         ctx.peer_barrier(flags_of_rank, self.rank, 2 * slot + 1)
         self.phase_c(sizeQl, gp_of_rank[self.rank], out)
+
+    # ---- limb-sharded rotation (EvalAutomorphism with automorphism index k) and rescale
+    def rotate(self, sizeQl, k, ct, evk_a, evk_b, tmp, out, gather_q, gather_p, all_gather):
+        L = lib()
+        _ck(L.ofhe_shard_rotate_a(self.h, sizeQl, _ptr(ct), _ptr(tmp), _ptr(gather_q), _stream()))
+        all_gather(gather_q)
+        self.phase_b(sizeQl, gather_q, evk_a, evk_b, gather_p)
+        all_gather(gather_p)
+        _ck(L.ofhe_shard_rotate_c(self.h, sizeQl, k, _ptr(gather_p), _ptr(tmp), _ptr(out), _stream()))
+
+    def rotate_push(self, sizeQl, k, ct, evk_a, evk_b, tmp, out, gq_of_rank, gp_of_rank, flags_of_rank, slot=0):
+        ctx, L = self.ring.ctx, lib()
+        _ck(L.ofhe_shard_rotate_a_push(self.h, sizeQl, _ptr(ct), _ptr(tmp), gq_of_rank, _stream()))
+        ctx.peer_barrier(flags_of_rank, self.rank, 2 * slot)
+        self.phase_b_push(sizeQl, evk_a, evk_b, gq_of_rank, gp_of_rank)
+        ctx.peer_barrier(flags_of_rank, self.rank, 2 * slot + 1)
+        _ck(L.ofhe_shard_rotate_c(self.h, sizeQl, k, gp_of_rank[self.rank], _ptr(tmp), _ptr(out), _stream()))
+
+    def rescale(self, sizeQl, ct, out, gather_l, broadcast):
+        """broadcast(buf, src_rank): the caller's collective (torch.distributed.broadcast in production)."""
+        L = lib()
+        _ck(L.ofhe_shard_rescale_a(self.h, sizeQl, _ptr(ct), _ptr(gather_l), _stream()))
+        broadcast(gather_l, (sizeQl - 1) % self.world)
+        _ck(L.ofhe_shard_rescale_b(self.h, sizeQl, _ptr(ct), _ptr(gather_l), _ptr(out), _stream()))
+
+    def rescale_push(self, sizeQl, ct, out, gl_of_rank, flags_of_rank, index=0):
+        ctx, L = self.ring.ctx, lib()
+        _ck(L.ofhe_shard_rescale_a_push(self.h, sizeQl, _ptr(ct), gl_of_rank, _stream()))
+        ctx.peer_barrier(flags_of_rank, self.rank, index)
+        _ck(L.ofhe_shard_rescale_b(self.h, sizeQl, _ptr(ct), gl_of_rank[self.rank], _ptr(out), _stream()))
 
     def evalmult(self, sizeQl, ct1, ct2, evk_a, evk_b, out, gather_q, gather_p, all_gather):
         self.phase_a(sizeQl, ct1, ct2, out, gather_q)
