@@ -44,9 +44,14 @@ struct Counters {
 
 class Runtime {
 public:
+    // The runtime is IMMORTAL (never destroyed): polynomials held by objects with static storage duration -- the
+    // reference keeps every CryptoContext and every evaluation key in static containers -- release their slabs during
+    // static destruction, i.e. possibly after a function-local static would already be gone; returning a slab to the
+    // pool of a destroyed runtime corrupted the heap at exit (tools/hal_bootstrap.cpp, which does not call
+    // ReleaseAllContexts as the gtest suites do).  The tallies are printed by an atexit handler instead.
     static Runtime& Get() {
-        static Runtime r;
-        return r;
+        static Runtime* r = new Runtime();
+        return *r;
     }
     ofhe_ctx* ctx = nullptr;
 
@@ -151,16 +156,19 @@ private:
     Runtime() {
         const char* dev = std::getenv("OFHE_B200_DEVICE");
         Check(ofhe_ctx_create(dev ? std::atoi(dev) : 0, &ctx), "ofhe_ctx_create (no CUDA device: this backend has no CPU path)");
-    }
-    ~Runtime() {  // process exit tears the CUDA context down
         if (std::getenv("OFHE_B200_HAL_STATS"))
-            std::fprintf(stderr,
-                         "[ofhe_b200 hal] device work: limb_ntt=%llu ew_limbs=%llu automorph_limbs=%llu bconv=%llu "
-                         "rescale=%llu modup=%llu moddown=%llu h2d_bytes=%llu d2h_bytes=%llu\n",
-                         (unsigned long long)n.ntt, (unsigned long long)n.ew, (unsigned long long)n.automorph,
-                         (unsigned long long)n.bconv, (unsigned long long)n.rescale, (unsigned long long)n.modup,
-                         (unsigned long long)n.moddown, (unsigned long long)n.h2d_bytes, (unsigned long long)n.d2h_bytes);
+            std::atexit(&Runtime::PrintStats);
     }
+    static void PrintStats() {
+        const Counters& n = Get().n;
+        std::fprintf(stderr,
+                     "[ofhe_b200 hal] device work: limb_ntt=%llu ew_limbs=%llu automorph_limbs=%llu bconv=%llu "
+                     "rescale=%llu modup=%llu moddown=%llu h2d_bytes=%llu d2h_bytes=%llu\n",
+                     (unsigned long long)n.ntt, (unsigned long long)n.ew, (unsigned long long)n.automorph,
+                     (unsigned long long)n.bconv, (unsigned long long)n.rescale, (unsigned long long)n.modup,
+                     (unsigned long long)n.moddown, (unsigned long long)n.h2d_bytes, (unsigned long long)n.d2h_bytes);
+    }
+    ~Runtime() {}  // never runs, see Get(): process exit tears the CUDA context down
     static constexpr size_t kPoolCapWords = (size_t)3 << 30;  // 24 GiB of cached slabs
     std::mutex pool_mu_;
     std::map<size_t, std::vector<uint64_t*>> pool_;
