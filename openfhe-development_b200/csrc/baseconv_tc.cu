@@ -4,7 +4,7 @@
 //     out_j[r] = ( sum_i y_i[r] * M[i][j] )  mod p_j,      y_i = x_i * QHatInvModq_i mod q_i,  M[i][j] = QHatModp[i][j]
 //
 // is, for every target limb j, an exact 124-bit integer dot product over <= 16 source limbs followed by one
-// 128 -> 64 Barrett step.  The CUDA-core kernel (baseconv.cu) spends 3 IMAD.WIDE + a 64-bit add per 60x60-bit MAC
+// reduction mod p_j.  The CUDA-core kernel (baseconv.cu) spends 3 IMAD.WIDE + a 64-bit add per 60x60-bit MAC
 // (215 SASS instructions per output residue, measured).  Here the dot products run on tcgen05.mma kind::i8:
 //
 //   * residues and matrix entries are split into their 8 bytes -- no work, the bytes of the 64-bit words ARE the
@@ -20,12 +20,16 @@
 //     with t < 2p because S' < 16 * 2^60 * p, then one conditional subtraction: the canonical residue, bit for bit
 //     the value of the reference's 128-bit accumulate + BarrettUint128ModUint64.
 //
-// One persistent CTA per SM: 512 threads, all 512 TMEM columns as two 256-column accumulator buffers (16 target limbs
-// each), the whole B image of the job (<= 5 chunks of 32 KiB) and two 16 KiB A tiles in shared memory.  Thread 0
-// issues the MMAs (4 x M128 N256 K32 per chunk) and commits them to an mbarrier per buffer; all 16 warps run the
+// One persistent CTA per SM, 17 warps: all 512 TMEM columns as two 256-column accumulator buffers (16 target limbs
+// each), the whole B image of the job (<= 5 chunks of 32 KiB) and two 16 KiB A tiles in shared memory.  Warp 16 issues
+// the MMAs (4 x M128 N256 K32 per chunk, tcgen05.commit onto the buffer's `full` mbarrier); warps 0..15 run the
 // epilogue of one buffer while the tensor core fills the other, and transpose the next tile ([limb][coefficient] in
-// HBM -> [coefficient][limb bytes] in shared memory) through registers.  Several conversions (the digits of a ModUp,
-// the two polynomials of a ModDown) are one launch: a job list, work = (job, polynomial, tile).
+// HBM -> [coefficient][limb bytes] in shared memory) through registers.  The warps meet only through mbarriers; a
+// job's tables and B image arrive by TMA bulk copies.  Several conversions (the digits of a ModUp, the two
+// polynomials of a ModDown) are one launch: a job list, work = (job, polynomial, tile), a contiguous share per CTA.
+// Measured on B200 (profiles/r02s_*): 15 -> 45 limbs at N = 2^16 in 20.9 us (CUDA cores: 50.2 us); the MMAs occupy the
+// tensor pipe 12 % of the time (kind::i8 issues at 8174 MAC/clk/SM, profiles/r02r_mma_rate.txt), the kernel is bound
+// by integer issue in the epilogue at ~52 SASS instructions per output residue.
 //
 // Eligibility: mode 0 (approximate conversion), <= 16 source limbs, N >= 128.  Everything else stays on baseconv.cu.
 #include <atomic>
@@ -47,7 +51,7 @@ constexpr int kChunkBytes = kChunkN * kK;         // 32 KiB of B per chunk
 constexpr int kTileBytes  = kTileM * kK;          // 16 KiB of A per tile
 constexpr int kMaxChunks  = 5;                    // 80 target limbs per job (larger conversions are split into jobs)
 constexpr int kMaxJobs    = 4;
-constexpr int kSub        = kEpiThreads / 128;     // warps per TMEM lane quarter
+constexpr int kSub        = kEpiThreads / 128;    // warps per TMEM lane quarter
 constexpr int kOutPerThr  = kChunkOut / kSub;     // outputs of a chunk per thread
 
 struct TcJob {
