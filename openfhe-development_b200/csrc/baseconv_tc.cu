@@ -44,12 +44,19 @@ namespace {
 constexpr int kEpiThreads = 512;                  // 16 transpose / epilogue warps
 constexpr int kTcThreads  = kEpiThreads + 32;     // + the MMA warp
 constexpr int kTileM      = 128;                  // coefficients per tile = TMEM lanes
-constexpr int kChunkOut   = 16;                   // target limbs per accumulator buffer
-constexpr int kChunkN     = 256;                  // columns per buffer: 16 limbs x 16 digit weights
+#ifndef OFHE_TC_NBUF
+#define OFHE_TC_NBUF 2  // accumulator buffers in TMEM: 2 x 256 columns (16 target limbs each) or 4 x 128 (8 each).
+                        // Measured (B200, 15 -> 45 limbs, N = 2^16): 20.9 us with 2, 22.9 us with 4 -- the extra slack for the
+                        // MMA warp costs twice the barrier traffic and halves the outputs per TMEM load; both bit-exact.
+#endif
+constexpr int kNBuf       = OFHE_TC_NBUF;
+static_assert(kNBuf == 2 || kNBuf == 4, "two or four accumulator buffers");
+constexpr int kChunkN     = 512 / kNBuf;          // columns per buffer: target limbs x 16 digit weights
+constexpr int kChunkOut   = kChunkN / 16;         // target limbs per accumulator buffer
 constexpr int kK          = 128;                  // 16 source limbs x 8 bytes
 constexpr int kChunkBytes = kChunkN * kK;         // 32 KiB of B per chunk
 constexpr int kTileBytes  = kTileM * kK;          // 16 KiB of A per tile
-constexpr int kMaxChunks  = 5;                    // 80 target limbs per job (larger conversions are split into jobs)
+constexpr int kMaxChunks  = 80 / kChunkOut;       // 80 target limbs per job (larger conversions are split into jobs)
 constexpr int kMaxJobs    = 4;
 constexpr int kSub        = kEpiThreads / 128;    // warps per TMEM lane quarter
 constexpr int kOutPerThr  = kChunkOut / kSub;     // outputs of a chunk per thread
@@ -206,8 +213,8 @@ __device__ __forceinline__ uint64_t fold_columns_fast(const uint32_t* v, uint64_
 struct TcTables {
     uint64_t dst[kMaxChunks * kChunkOut][4];  // p, -p^-1 mod 2^64, word offset of the output row, (pad)
     uint64_t src[16][4];                      // q, QHatInv, Shoup(QHatInv), word offset of the input row (~0: padding)
-    uint64_t full[2];                         // accumulator buffer written   (1 arrival: tcgen05.commit)
-    uint64_t empty[2];                        // accumulator buffer drained   (16 arrivals: one per epilogue warp)
+    uint64_t full[kNBuf];                     // accumulator buffer written   (1 arrival: tcgen05.commit)
+    uint64_t empty[kNBuf];                    // accumulator buffer drained   (16 arrivals: one per epilogue warp)
     uint64_t afull[2];                        // A tile staged                (16 arrivals)
     uint64_t job;                             // tables + B image of a job landed (bulk copies, byte count)
     uint32_t tmem_base;
@@ -233,11 +240,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kNBuf; ++b) {
             mbar_init(smem_u32(&tb->full[b]), 1);
             mbar_init(smem_u32(&tb->empty[b]), kEpiThreads / 32);
-            mbar_init(smem_u32(&tb->afull[b]), kEpiThreads / 32);
         }
+        for (int b = 0; b < 2; ++b)
+            mbar_init(smem_u32(&tb->afull[b]), kEpiThreads / 32);
         mbar_init(smem_u32(&tb->job), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
     uint32_t w           = (uint32_t)(((uint64_t)W * blockIdx.x) / gridDim.x);
     const uint32_t w_end = (uint32_t)(((uint64_t)W * (blockIdx.x + 1)) / gridDim.x);
     const uint32_t jobbar = smem_u32(&tb->job);
-    uint32_t g = 0, tcnt = 0, jcnt = 0;  // chunks / tiles / jobs this CTA has been through: accumulator buffer g & 1, A buffer tcnt & 1
+    uint32_t g = 0, tcnt = 0, jcnt = 0;  // chunks / tiles / jobs this CTA has been through: accumulator buffer g mod kNBuf, A buffer tcnt & 1
     int jb_loaded = -1;
     uint64_t nxt[4];
 
@@ -325,8 +333,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
             if (lane == 0) {
                 mbar_wait(afull0 + 8 * (tcnt & 1), (tcnt >> 1) & 1);
                 for (uint32_t ch = 0; ch < nch; ++ch, ++g) {
-                    const uint32_t b = g & 1;
-                    mbar_wait(empty0 + 8 * b, ((g >> 1) & 1) ^ 1);  // the first use of each buffer passes at once
+                    const uint32_t b = g % kNBuf;
+                    mbar_wait(empty0 + 8 * b, ((g / kNBuf) & 1) ^ 1);  // the first use of each buffer passes at once
                     tc_fence_after();
 #pragma unroll
                     for (uint32_t k = 0; k < kK / 32; ++k)
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bconv_tc_kernel(RingDev r, TcLa
             if (have_next)
                 load_a(J, local + 1, nxt);  // in flight during the first epilogue
             for (uint32_t ch = 0; ch < nch; ++ch, ++g) {
-                const uint32_t b = g & 1;
-                mbar_wait(full0 + 8 * b, (g >> 1) & 1);
+                const uint32_t b = g % kNBuf;
+                mbar_wait(full0 + 8 * b, (g / kNBuf) & 1);
                 tc_fence_after();
                 // this thread: outputs [4 sub, 4 sub + 4) of the chunk, as two pairs; the second pair's load is in
                 // flight while the first pair is folded and reduced, and the two reductions of a pair are independent
